@@ -1,0 +1,143 @@
+/*
+ * radlite_b200.h -- C ABI of the B200-native RADLite line ray-tracer (libradlite_b200.so).
+ *
+ * The reference (pontoppi/radlite, Fortran 77) has no FFI for this path: everything is
+ * `call` + COMMON blocks.  The seam this ABI replaces is the body of the line loop
+ *   main.F:1043-1049   do iln ... call calc_line_spectrum(iln,...)
+ *   telescope.F:1465   calc_line_spectrum  -> :1320 calc_freq_flux_observer
+ *   telescope.F:339    make_image_circular -> :2787 make_trajectory_c, :3889 charintline
+ * i.e. "given the COMMON state, fill imcir_int / imcir_cmask / spec_flux_observer for line
+ * iline", widened to a batch of lines.  Each entry point below names the reference routine /
+ * COMMON arrays it takes over.  INTEGRATION.md shows the iso_c_binding interface module and the
+ * patch to telescope.F/main.F that binds them.
+ *
+ * Conventions
+ *  - every pointer is HOST memory owned by the caller; the library copies during the call.
+ *  - arrays are dense, C order, 0-based.  "cell" arrays are [ir][it] with it fastest over the
+ *    stored (upper) hemisphere, i.e. exactly the memory order of the Fortran (it,ir) arrays once
+ *    the unused padding of the COMPILE-TIME dimensions is squeezed out (the Fortran shim packs).
+ *  - return value 0 = ok; otherwise the reference's `stop` code where one exists (13, 749, 393,
+ *    6023/6024, 124, 137, 7454, 83991/91991, 192, 987/988 ...) or 1 for a bare `stop`;
+ *    negative values are CUDA/runtime failures.  rl_last_error() gives the message; the Fortran
+ *    shim prints it and STOPs with the same code, so drivers see the same behaviour
+ *    (missing radlite.success).
+ *  - one ctx per process and per GPU, calls serialised by the caller (the reference is
+ *    single-threaded and not re-entrant).
+ *  - there is NO CPU fallback: rl_create fails if no sm_100 device is usable.
+ */
+#ifndef RADLITE_B200_H
+#define RADLITE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rl_ctx rl_ctx;
+
+/* device = CUDA ordinal (one process per GPU: pass LOCAL_RANK) */
+int  rl_create(rl_ctx **out, int device);
+void rl_destroy(rl_ctx *ctx);
+const char *rl_last_error(const rl_ctx *ctx);
+
+/* grid.F:711-819 + 1098-1210 (create_spacegrid, radius.inp/theta.inp branches, mirror flag 1):
+ * r[nr] cm, theta[nth] rad (upper hemisphere); ghost cells rsi_x_c(-1:0), (n+1:n+2) and the
+ * theta mirror are built inside with the reference's literals.  Also does interpol.F:87-100
+ * (make_index -> ridx_it). */
+int rl_set_grid(rl_ctx *ctx, int nr, int nth, const double *r, const double *theta);
+/* the Fortran host passes rsi_x_c(-1,1) and rsi_x_c(-1,2) as they are (common_grid.h:17);
+ * nt = irsi_frsizey (both hemispheres). */
+int rl_set_grid_ghosted(rl_ctx *ctx, int nr, int nt, const double *rc_m1, const double *tc_m1);
+
+/* COMMON /mediumarr/ medium_arr_rho, medium_arr_velocity (common_setup.h:25-29),
+ * /localabundance/ locabun_abund_mol (common_lines.h:133), locprof_linewidth(1,it,ir)
+ * (setup.F:803-850: line independent), umass_av (line.F:142).
+ * rho, abund, linewidth: [nr][nth]; vel: [nr][nth][3] (v_r, v_theta, v_phi) cm/s. */
+int rl_set_medium(rl_ctx *ctx, const double *rho, const double *abund, const double *vel,
+                  const double *linewidth, double umass_av);
+
+/* COMMON lev_up, lev_down, linefreq, Aud_const, gdeg (line.F:1826-1985 read_species_lambda)
+ * and line_level_popul(lev,it,ir) (line.F:811-950 read_levelpopul): popul [nr][nth][nlevels].
+ * Takes over line.F:1600-1673 global_prepare_transitions / 1708-1788 prepare_lines (Bud,Bdu). */
+int rl_set_lines(rl_ctx *ctx, int nlines, int nlevels, const int *lev_up, const int *lev_down,
+                 const double *linefreq, const double *aud, const double *gdeg,
+                 const double *popul);
+
+/* Takes over line.F:3687-3743 global_prepare_line_dust / 3502-3608 line_dust_compute_src_alp
+ * and setup.F:937 bplanck (the source.F dust source term).  COMMON dust_rho(spec,it,ir),
+ * dust_temp(size,spec,it,ir), dust_kappawgt_abs/scat(freq,1,size,spec), cont_freq_nu,
+ * scati_src(freq,it,ir) (source.F:494 read_scatsource; NULL = all zero).
+ * nsize[nspec]; kappa_*: [nspec][maxsize][ncf]; dust_rho: [nr][nth][nspec];
+ * dust_temp: [nr][nth][nspec][maxsize]; scati_src: [nr][nth][ncf]. Call after rl_set_lines. */
+int rl_set_dust(rl_ctx *ctx, int nspec, const int *nsize, int ncf, const double *cont_freq_nu,
+                const double *kappa_abs, const double *kappa_scat, const double *dust_rho,
+                const double *dust_temp, const double *scati_src);
+/* alternative for a host that already ran global_prepare_line_dust:
+ * line_dust_src(1,iline,it,ir), line_dust_alp(1,iline,it,ir) as [nlines][nr][nth] */
+int rl_set_line_dust(rl_ctx *ctx, const double *src, const double *alp);
+
+/* telescope.F:715-1191 setup_rays_circular(1,nr,1,anginf,nrphiinf,nrext,dbdr,rstar,imethod,nrref)
+ * (call site main.F:792; imethod=1, nrref=10 are hard-wired at main.F:37-38) and the ring
+ * edges of telescope.F:443-488. */
+int rl_set_camera(rl_ctx *ctx, double anginf, int nphi, int nrext, int dbdr, double rstar,
+                  int imethod, int nrref);
+
+/* iradbnd_in_itype / iradbnd_out_itype (common_boundary.h), radbnd_cont_starspec on
+ * cont_freq_nu (star.F:449-528; surface intensity), radbnd_cont_interstellfield (star.F:675;
+ * NULL unless out_itype==3).  Takes over line.F:3797-3845 / 3855-3903 per line. */
+int rl_set_bc(rl_ctx *ctx, int in_itype, int out_itype, int ncf, const double *cont_freq_nu,
+              const double *starspec_cont, const double *isrf_cont);
+
+/* configure.h:8 SUBGRID, :53 NONREDUNDANT, :52 LEVTHRES as run-time switches; aksmax from
+ * line.F:2968-3033 line_velo_prep_profiles_abun (pass <0 to have it computed). */
+int rl_set_options(rl_ctx *ctx, int subgrid, int nonredundant, double levthres, double aksmax);
+
+/* rays_nrr, rays_nrphi, rays_amount (common_telescope.h:20-23) */
+int rl_get_camera_dims(rl_ctx *ctx, int *nrr, int *nphi, int *nray);
+/* rays_r(0:nrr), imcir_ri(0:nrr+1) */
+int rl_get_rings(rl_ctx *ctx, double *rays_r, double *imcir_ri);
+
+/* main.F:1043-1049 for lines iline0 .. iline0+nl-1 (1-based):
+ *   nfr, vmax_kms = main_passbnfr, main_passbwidth (main.F:209-211); dist_cm (main.F:213)
+ *   flux       [nl][nfr]               spec_flux_observer(inu)           (required)
+ *   imcir      [nl][nrr+1][nphi][nfr]  imcir_int(inu,iphi,ir)            (NULL = not wanted)
+ *   cmask      [nl][nrr+1][nphi][nfr]  imcir_cmask (accumulates over lines like the reference)
+ *   tau_center [nl]                    char_tau_center
+ *   maserflag  [nl]                    maserflag (telescope.F:4295)
+ *   velo       [nl][nfr]               line_dnu(inu,iline)/line_nu0(iline)
+ * Channel order is the reference's inu = 1..nfr (ascending frequency). */
+int rl_render(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
+              double *flux, double *imcir, int *cmask, double *tau_center, int *maserflag,
+              double *velo);
+
+/* work counters since the last reset: R = ray-channel integrations (charintline calls the
+ * reference would make), E = element integrations (integrate_element_linedust calls incl.
+ * sub-grid steps), S = ray segments visited. */
+void rl_get_counters(const rl_ctx *ctx, double *R, double *E, double *S);
+void rl_reset_counters(rl_ctx *ctx);
+
+/* ---- device-resident variant used by bench.py's kernel-only timing ----------------------
+ * Same work as rl_render but inputs stay resident and nothing is copied back: the result stays
+ * in device memory until rl_fetch_flux.  kernel_ms[5] (optional) receives CUDA-event times [ms]
+ * on the library's stream: {geometry, per-line preparation + channel selection, the ray-integration kernel,
+ * continuum fill + flux reduction, whole call}. */
+int rl_render_device(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
+                     float *kernel_ms);
+int rl_fetch_flux(rl_ctx *ctx, int nl, int nfr, double *flux);
+/* forget the cached ray geometry so the next render rebuilds it (the reference rebuilds it for
+ * every ray of every line, telescope.F:500,538) */
+void rl_invalidate_geometry(rl_ctx *ctx);
+/* measured FP64 FMA throughput of this GPU [TFLOP/s] (DFMA chains, best of 4): the roofline
+ * denominator bench.py reports against (MEASURED_PEAKS.json carries no FP64 figure) */
+int rl_fp64_peak(rl_ctx *ctx, double *tflops);
+/* number of kernels this library launched since rl_create (bench.py "gpu_launches") */
+long long rl_launch_count(const rl_ctx *ctx);
+/* diagnostics: nodes of ray iray (1-based) as built on the device; arrays sized rl_max_nodes() */
+int rl_max_nodes(const rl_ctx *ctx);
+int rl_get_ray_nodes(rl_ctx *ctx, int iray, double *ds, double *dvmu, double *lw, double *wr,
+                     double *wt, int *cells4, int *flags);
+long long rl_total_nodes(const rl_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -90,6 +90,8 @@ struct orc_ctx {
   double *rrgrid, *ttgrid;
   /* counters */
   double cnt_R, cnt_E, cnt_S;
+  /* bounded-sample benchmarking: only rings ring_lo..ring_hi are traced (0,0 = all) */
+  int ring_lo, ring_hi, ring_stride;
 };
 
 #define RC(i) (c->rc[(i) + 1])
@@ -322,12 +324,18 @@ static void free_traj(orc_ctx *c) {
   free(c->th_radius); free(c->th_theta); free(c->th_s); free(c->r_radius); free(c->r_theta);
   free(c->r_s); free(c->sar1); free(c->sar2); free(c->th_ir); free(c->th_itheta);
   free(c->r_ir); free(c->r_itheta); free(c->iyar); free(c->rrgrid); free(c->ttgrid);
-  c->tr_s = 0;
+  c->tr_s = c->tr_radius = c->tr_theta = c->tr_mu = c->tr_phi = 0;
+  c->tr_icross = c->tr_iradius = c->tr_itheta = 0;
+  c->th_radius = c->th_theta = c->th_s = c->r_radius = c->r_theta = c->r_s = c->sar1 = c->sar2 = 0;
+  c->th_ir = c->th_itheta = c->r_ir = c->r_itheta = c->iyar = 0;
+  c->rrgrid = c->ttgrid = 0;
 }
 static void free_cam(orc_ctx *c) {
   free(c->rp_x0); free(c->rp_z0); free(c->rp_theta0); free(c->rp_s0); free(c->rays_r);
   free(c->imcir_r); free(c->imcir_ri); free(c->minvel); free(c->maxvel); free(c->cmask_persist);
-  c->rp_x0 = 0; c->cmask_persist = 0; c->cam_set = 0;
+  c->rp_x0 = c->rp_z0 = c->rp_theta0 = c->rp_s0 = c->rays_r = c->imcir_r = c->imcir_ri = 0;
+  c->minvel = c->maxvel = 0;
+  c->cmask_persist = 0; c->cam_set = 0;
 }
 void orc_destroy(orc_ctx *c) {
   if (!c) return;
@@ -1499,6 +1507,11 @@ static void render_line(orc_ctx *c, int iline, int nfr, double passband, double 
   for (ir = 1; ir <= nrr; ir++)
     for (iphi = 1; iphi <= nphi; iphi++) {
       double *cont = &imcir_cont[(size_t)ir * nphi + (iphi - 1)];
+      if (c->ring_hi > 0 && (ir < c->ring_lo || ir > c->ring_hi || (ir - c->ring_lo) % c->ring_stride != 0)) { /* benchmark sampling only */
+        for (inu = 1; inu <= nfr; inu++) imcir_int[IMIDX(inu, iphi, ir)] = 0.0;
+        iray = iray + 1;
+        continue;
+      }
       make_trajectory_c(c, c->rp_x0[iray], c->rp_z0[iray], c->rp_theta0[iray], c->rp_s0[iray]);
       inu = 1;
       imcir_int[IMIDX(inu, iphi, ir)] = charintline(c, iline, inu, iray, -1.0);
@@ -1600,6 +1613,11 @@ void orc_get_counters(const orc_ctx *c, double *R, double *E, double *S) {
   if (S) *S = c->cnt_S;
 }
 void orc_reset_counters(orc_ctx *c) { c->cnt_R = c->cnt_E = c->cnt_S = 0.0; }
+void orc_set_ring_sample(orc_ctx *c, int lo, int hi, int stride) {
+  c->ring_lo = lo;
+  c->ring_hi = hi;
+  c->ring_stride = stride > 0 ? stride : 1;
+}
 
 int orc_max_nodes(const orc_ctx *c) { return c->raysize; }
 

@@ -81,6 +81,9 @@ int orc_render(orc_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double 
  * E = calls of integrate_element_linedust, S = segments visited (sum over charintline calls) */
 void orc_get_counters(const orc_ctx *c, double *R, double *E, double *S);
 void orc_reset_counters(orc_ctx *c);
+/* benchmarking only: trace rings lo, lo+stride, .. <= hi (1-based) and leave the others zero; hi=0 = all.
+ * Gives a bounded sample of a workload for bench.py's cpu_baseline; never used by parity tests. */
+void orc_set_ring_sample(orc_ctx *c, int lo, int hi, int stride);
 
 /* camera tables after set_camera+set_grid: rays_r[0..nrr], imcir_ri[0..nrr+1] (telescope.F:443-488) */
 int orc_get_rings(orc_ctx *c, double *rays_r, double *imcir_ri);

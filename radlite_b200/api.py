@@ -1,0 +1,108 @@
+"""Host-side access to the CUDA library through its C ABI (include/radlite_b200.h).
+
+``Renderer`` is a thin ctypes object over ``libradlite_b200.so``.  There is no CPU fallback: if the
+library has not been built (``python -c 'import __graft_entry__ as g; g.build()'``) or no B200 is
+visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._binding import Binding, RadliteError, _d, _i
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libradlite_b200.so")
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                "(make -C radlite_b200/csrc).  radlite_b200 has no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rl_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        _lib.rl_create.restype = C.c_int
+        _lib.rl_render_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                          C.c_double, C.POINTER(C.c_float)]
+        _lib.rl_render_device.restype = C.c_int
+        _lib.rl_fetch_flux.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        _lib.rl_fetch_flux.restype = C.c_int
+        _lib.rl_launch_count.argtypes = [C.c_void_p]
+        _lib.rl_launch_count.restype = C.c_longlong
+        _lib.rl_total_nodes.argtypes = [C.c_void_p]
+        _lib.rl_total_nodes.restype = C.c_longlong
+        _lib.rl_max_nodes.argtypes = [C.c_void_p]
+        _lib.rl_max_nodes.restype = C.c_int
+        _lib.rl_get_ray_nodes.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 5 + [
+            C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib.rl_get_ray_nodes.restype = C.c_int
+    return _lib
+
+
+class Renderer(Binding):
+    """One context on one GPU (one process per GPU: pass LOCAL_RANK as ``device``)."""
+
+    def __init__(self, device: int = 0):
+        lib = load_library()
+        try:
+            super().__init__(lib, "rl_", create_args=(int(device),))
+        except RadliteError as e:
+            raise RuntimeError(
+                f"rl_create(device={device}) failed with {e.code}: no usable sm_100 GPU "
+                "(radlite_b200 has no CPU fallback)") from e
+
+    def render_device(self, iline0, nl, nfr, vmax_kms, dist_cm):
+        """Kernel-only pass: inputs resident, nothing copied back.  Returns CUDA-event times [ms]
+        of (geometry, per-line preparation, ray integration, flux reduction, whole call)."""
+        ms = (C.c_float * 5)()
+        self._check(self.lib.rl_render_device(self.ctx, int(iline0), int(nl), int(nfr),
+                                              float(vmax_kms), float(dist_cm), ms))
+        return [float(x) for x in ms]
+
+    def invalidate_geometry(self):
+        self.lib.rl_invalidate_geometry.argtypes = [C.c_void_p]
+        self.lib.rl_invalidate_geometry.restype = None
+        self.lib.rl_invalidate_geometry(self.ctx)
+
+    def fp64_peak_tflops(self) -> float:
+        self.lib.rl_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self.lib.rl_fp64_peak.restype = C.c_int
+        v = C.c_double()
+        self._check(self.lib.rl_fp64_peak(self.ctx, C.byref(v)))
+        return v.value
+
+    def fetch_flux(self, nl, nfr):
+        out = np.zeros((nl, nfr))
+        self._check(self.lib.rl_fetch_flux(self.ctx, int(nl), int(nfr), _d(out)))
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.rl_launch_count(self.ctx))
+
+    def total_nodes(self) -> int:
+        return int(self.lib.rl_total_nodes(self.ctx))
+
+    def ray_nodes(self, iray):
+        """Device-built node list of ray ``iray`` (1-based; 1 = centre)."""
+        n = max(1, int(self.lib.rl_max_nodes(self.ctx)))
+        # geometry may not be built yet: the first call sizes it
+        probe = self.lib.rl_get_ray_nodes(self.ctx, int(iray), None, None, None, None, None, None,
+                                          None)
+        if probe < 0:
+            self._check(-probe)
+        n = max(n, probe, int(self.lib.rl_max_nodes(self.ctx)))
+        ds, dvmu, lw, wr, wt = (np.zeros(n) for _ in range(5))
+        cells = np.zeros((n, 4), dtype=np.int32)
+        flags = np.zeros(n, dtype=np.int32)
+        k = self.lib.rl_get_ray_nodes(self.ctx, int(iray), _d(ds), _d(dvmu), _d(lw), _d(wr),
+                                      _d(wt), _i(cells), _i(flags))
+        if k < 0:
+            self._check(-k)
+        return dict(ds=ds[:k], dvmu=dvmu[:k], lw=lw[:k], wr=wr[:k], wt=wt[:k], cells=cells[:k],
+                    flags=flags[:k])

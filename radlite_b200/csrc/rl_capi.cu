@@ -1,0 +1,982 @@
+// rl_capi.cu -- host side of libradlite_b200: the C ABI of include/radlite_b200.h.
+//
+// Holds the model in HBM, builds the camera (telescope.F:715-1191, 443-488), the per-line
+// passband / boundary tables (line.F:427-545, 3797-3903), and drives the kernels of rl_geom.cu
+// and rl_render.cu.  No CPU implementation of the path lives here: without a usable sm_100
+// device rl_create fails.
+#include "../../include/radlite_b200.h"
+#include "rl_types.h"
+
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace rl {
+void launch_geom(const GeomParams &P, bool count, cudaStream_t st);
+void launch_prep(const PrepParams &P, cudaStream_t st);
+void launch_span(const RenderParams &P, cudaStream_t st);
+void launch_integrate(const RenderParams &P, unsigned total_items, cudaStream_t st);
+void launch_fill(const RenderParams &P, cudaStream_t st);
+void launch_center_replicate(const RenderParams &P, cudaStream_t st);
+void launch_flux(const RenderParams &P, const double *surf, double *ring, double dist2, double *flux,
+                 cudaStream_t st);
+void launch_cmask(const RenderParams &P, unsigned char *accum, int *out, cudaStream_t st);
+void launch_dfma_peak(double *sink, int iters, int blocks, int threads, cudaStream_t st);
+}  // namespace rl
+
+using namespace rl;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const T *h, size_t count, cudaStream_t st) {
+    cudaError_t e = ensure(count);
+    if (e != cudaSuccess) return e;
+    if (!count) return cudaSuccess;
+    return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
+  }
+  cudaError_t upload(const std::vector<T> &h, cudaStream_t st) { return upload(h.data(), h.size(), st); }
+};
+
+}  // namespace
+
+struct rl_ctx {
+  std::string err;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long launches = 0;
+  // grid
+  int nr = 0, nt = 0, nth = 0;
+  std::vector<double> rc, tc;
+  std::vector<int> ridx;
+  DevBuf<double> d_rc, d_tc;
+  DevBuf<int> d_ridx;
+  // medium
+  bool have_medium = false;
+  double umass_av = 0;
+  std::vector<double> h_lw;
+  DevBuf<double> d_rho, d_abund;
+  DevBuf<double4> d_cellS;
+  // lines
+  int nlines = 0, nlevels = 0;
+  std::vector<int> lev_up, lev_down;
+  std::vector<double> linefreq, aud, gdeg, bud, bdu;
+  DevBuf<double> d_popul;
+  // dust
+  bool have_dust = false, have_line_dust = false;
+  int nspec = 0, maxsize = 0, ncf_d = 0;
+  std::vector<int> nsize;
+  std::vector<double> cfreq_d;
+  DevBuf<int> d_nsize;
+  DevBuf<double> d_kabs, d_kscat, d_drho, d_dtemp, d_scat;
+  bool have_scat = false;
+  std::vector<double> h_ld_src, h_ld_alp;  // only for rl_set_line_dust
+  // camera
+  bool cam_set = false;
+  double anginf = 0, rstar = 0, theta0 = 0;
+  int nphi = 0, nrext = 0, dbdr = 1, imethod = 1, nrref = 10;
+  int nray = 0, nrr = 0;
+  std::vector<double> rp_x0, rp_z0, rays_r, imcir_ri, surf;
+  DevBuf<double> d_x0, d_z0, d_surf;
+  // boundary
+  bool bc_set = false;
+  int in_itype = 2, out_itype = 0;
+  std::vector<double> cfreq_b, starspec_cont, isrf_cont;
+  // options
+  int subgrid = 1, nonredundant = 1;
+  double levthres = 1e-3, aksmax_opt = -1.0;
+  // geometry
+  bool geom_valid = false;
+  long long total_nodes = 0;
+  int max_nodes = 0;
+  DevBuf<int> d_node_cnt;
+  DevBuf<long long> d_node_off;
+  std::vector<long long> h_node_off;
+  DevBuf<double> d_nds, d_ndvmu, d_nlw, d_nwr, d_nwt;
+  DevBuf<int4> d_ncell;
+  DevBuf<uint32_t> d_nflag;
+  DevBuf<int> d_status;
+  // render buffers
+  DevBuf<double4> d_cellL;
+  DevBuf<LineDev> d_lines;
+  DevBuf<double> d_line_dnu, d_velo, d_star_line, d_isrf_line;
+  DevBuf<int> d_lev_up, d_lev_down, d_inudust;
+  DevBuf<double> d_wgt, d_freq, d_ld_src, d_ld_alp;
+  DevBuf<int4> d_rng;
+  DevBuf<unsigned int> d_nitems, d_item_off;
+  DevBuf<unsigned char> d_scan_tmp;
+  DevBuf<double> d_img, d_ring, d_flux, d_tau;
+  DevBuf<unsigned char> d_integ, d_cmask_accum;
+  DevBuf<int> d_cmask_out;
+  DevBuf<int> d_maser;
+  DevBuf<unsigned long long> d_counters;
+  long long cmask_accum_n = 0;
+  double cnt[3] = {0, 0, 0};
+  std::vector<double> last_flux;
+  int last_nl = 0, last_nfr = 0;
+};
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      char b_[512];                                                                       \
+      snprintf(b_, sizeof b_, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, \
+               __LINE__, cudaGetErrorString(e_));                                         \
+      c->err = b_;                                                                        \
+      return -(int)e_ - 1000;                                                             \
+    }                                                                                     \
+  } while (0)
+
+static int fail(rl_ctx *c, int code, const char *msg) {
+  char b[512];
+  snprintf(b, sizeof b, "stop %d: %s", code, msg);
+  c->err = b;
+  return code ? code : 1;
+}
+
+// nrecip.F:157 hunt started from an out-of-range guess: pure bisection, xx(1..n) ascending
+static int hunt_host(const double *xx1, int n, double x) {
+  int jlo = 0, jhi = n + 1;
+  const bool ascnd = xx1[n - 1] > xx1[0];
+  while (jhi - jlo != 1) {
+    int jm = (jhi + jlo) / 2;
+    if ((x > xx1[jm - 1]) == ascnd) jlo = jm;
+    else jhi = jm;
+  }
+  return jlo;
+}
+
+extern "C" {
+
+int rl_create(rl_ctx **out, int device) {
+  if (!out) return 13;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return -1;  // no CPU fallback
+  if (device < 0 || device >= ndev) return -2;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -3;
+  if (prop.major < 10) return -4;  // built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return -5;
+  rl_ctx *c = new rl_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return -6;
+  }
+  for (auto &e : c->ev) cudaEventCreate(&e);
+  c->d_status.ensure(1);
+  c->d_counters.ensure(3);
+  cudaMemsetAsync(c->d_counters.p, 0, 3 * sizeof(unsigned long long), c->st);
+  cudaStreamSynchronize(c->st);
+  *out = c;
+  return 0;
+}
+
+void rl_destroy(rl_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  for (auto &e : c->ev)
+    if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(c->st);
+  delete c;
+}
+
+const char *rl_last_error(const rl_ctx *c) { return c ? c->err.c_str() : "null ctx"; }
+
+int rl_set_grid_ghosted(rl_ctx *c, int nr, int nt, const double *rc_m1, const double *tc_m1) {
+  if (nr < 2 || nt < 2 || (nt & 1)) return fail(c, 13, "set_grid: bad sizes");
+  cudaSetDevice(c->device);
+  c->nr = nr;
+  c->nt = nt;
+  c->nth = nt / 2;
+  c->rc.assign(rc_m1, rc_m1 + nr + 4);
+  c->tc.assign(tc_m1, tc_m1 + nt + 4);
+  // interpol.F:87-100 make_index (MIRROR_THETA)
+  c->ridx.resize(nt + 9);
+  for (int it = -4; it <= nt + 4; it++) {
+    int v = it;
+    if (v < 1) v = 1 - v;
+    if (v > nt) v = 2 * nt + 1 - v;
+    if (v > nt / 2) v = nt + 1 - v;
+    c->ridx[it + 4] = v;
+  }
+  CU(c->d_rc.upload(c->rc, c->st));
+  CU(c->d_tc.upload(c->tc, c->st));
+  CU(c->d_ridx.upload(c->ridx, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->geom_valid = false;
+  c->cam_set = false;
+  c->have_medium = false;
+  c->nlines = 0;
+  c->have_dust = c->have_line_dust = false;
+  c->cmask_accum_n = 0;
+  return 0;
+}
+
+int rl_set_grid(rl_ctx *c, int nr, int nth, const double *r, const double *theta) {
+  if (nr < 2 || nth < 1) return fail(c, 13, "set_grid: bad sizes");
+  const int nt = 2 * nth;
+  std::vector<double> rc(nr + 4), tc(nt + 4);
+  auto R = [&](int i) -> double & { return rc[i + 1]; };
+  auto T = [&](int i) -> double & { return tc[i + 1]; };
+  for (int i = 1; i <= nr; i++) R(i) = r[i - 1];
+  // grid.F:772-777
+  R(0) = R(1) * R(1) / R(2);
+  R(-1) = R(0) * R(0) / R(1);
+  R(nr + 1) = R(nr) * R(nr) / R(nr - 1);
+  R(nr + 2) = R(nr + 1) * R(nr + 1) / R(nr);
+  // grid.F:1147-1176 (mirror with 3.14159265359d0, upper ghosts with single-precision 2*pi)
+  for (int i = 1; i <= nth; i++) T(i) = theta[i - 1];
+  for (int i = 1; i <= nth; i++) T(2 * nth + 1 - i) = 3.14159265359 - T(i);
+  T(0) = -T(1);
+  T(-1) = -T(2);
+  const float twopi_f = 2 * 3.1415926e0f;
+  T(nt + 1) = (double)twopi_f - T(nt);
+  T(nt + 2) = (double)twopi_f - T(nt - 1);
+  return rl_set_grid_ghosted(c, nr, nt, rc.data(), tc.data());
+}
+
+int rl_set_medium(rl_ctx *c, const double *rho, const double *abund, const double *vel,
+                  const double *linewidth, double umass_av) {
+  if (!c->nr) return fail(c, 13, "set_medium: call set_grid first");
+  cudaSetDevice(c->device);
+  const size_t n = (size_t)c->nr * c->nth;
+  std::vector<double4> cs(n);
+  for (size_t i = 0; i < n; i++) cs[i] = make_double4(linewidth[i], vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+  c->h_lw.assign(linewidth, linewidth + n);
+  CU(c->d_cellS.upload(cs.data(), n, c->st));
+  CU(c->d_rho.upload(rho, n, c->st));
+  CU(c->d_abund.upload(abund, n, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->umass_av = umass_av;
+  c->have_medium = true;
+  c->geom_valid = false;
+  return 0;
+}
+
+int rl_set_lines(rl_ctx *c, int nlines, int nlevels, const int *lev_up, const int *lev_down,
+                 const double *linefreq, const double *aud, const double *gdeg, const double *popul) {
+  if (!c->nr) return fail(c, 13, "set_lines: call set_grid first");
+  // line.F:1720-1762 checks
+  if (nlines < 1) return fail(c, 13, "Minimum of 1 line!");
+  if (nlevels < 2) return fail(c, 13, "Minimum of 2 levels!");
+  for (int i = 0; i < nlines; i++) {
+    if (lev_up[i] < 1 || lev_down[i] < 1 || lev_up[i] > nlevels || lev_down[i] > nlevels)
+      return fail(c, 13, "line levels should be within the range 1..nlevels");
+    if (lev_up[i] <= lev_down[i]) return fail(c, 13, "The lines should be given from upper to lower level");
+    if (linefreq[i] == 0.0) return fail(c, 13, "HUH?? Somehow linefreq() is 0.d0?");
+  }
+  cudaSetDevice(c->device);
+  c->nlines = nlines;
+  c->nlevels = nlevels;
+  c->lev_up.assign(lev_up, lev_up + nlines);
+  c->lev_down.assign(lev_down, lev_down + nlines);
+  c->linefreq.assign(linefreq, linefreq + nlines);
+  c->aud.assign(aud, aud + nlines);
+  c->gdeg.assign(gdeg, gdeg + nlevels);
+  c->bud.resize(nlines);
+  c->bdu.resize(nlines);
+  for (int i = 0; i < nlines; i++) {  // line.F:1770-1788
+    const double gratio = gdeg[lev_up[i] - 1] / gdeg[lev_down[i] - 1];
+    c->bud[i] = 6.78171833781e46 * aud[i] / (linefreq[i] * linefreq[i] * linefreq[i]);
+    c->bdu[i] = c->bud[i] * gratio;
+  }
+  CU(c->d_popul.upload(popul, (size_t)c->nr * c->nth * nlevels, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->have_line_dust = false;
+  return 0;
+}
+
+int rl_set_dust(rl_ctx *c, int nspec, const int *nsize, int ncf, const double *cont_freq_nu,
+                const double *kappa_abs, const double *kappa_scat, const double *dust_rho,
+                const double *dust_temp, const double *scati_src) {
+  if (!c->nlines) return fail(c, 13, "set_dust: call set_lines first");
+  cudaSetDevice(c->device);
+  int maxsize = 0;
+  for (int i = 0; i < nspec; i++) maxsize = std::max(maxsize, nsize[i]);
+  const size_t ncell = (size_t)c->nr * c->nth;
+  c->nspec = nspec;
+  c->maxsize = maxsize;
+  c->ncf_d = ncf;
+  c->nsize.assign(nsize, nsize + nspec);
+  c->cfreq_d.assign(cont_freq_nu, cont_freq_nu + ncf);
+  CU(c->d_nsize.upload(c->nsize, c->st));
+  CU(c->d_kabs.upload(kappa_abs, (size_t)nspec * maxsize * ncf, c->st));
+  CU(c->d_kscat.upload(kappa_scat, (size_t)nspec * maxsize * ncf, c->st));
+  CU(c->d_drho.upload(dust_rho, ncell * nspec, c->st));
+  CU(c->d_dtemp.upload(dust_temp, ncell * nspec * maxsize, c->st));
+  c->have_scat = scati_src != nullptr;
+  if (scati_src) CU(c->d_scat.upload(scati_src, ncell * ncf, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->have_dust = true;
+  c->have_line_dust = false;
+  return 0;
+}
+
+int rl_set_line_dust(rl_ctx *c, const double *src, const double *alp) {
+  if (!c->nlines) return fail(c, 13, "set_line_dust: call set_lines first");
+  const size_t n = (size_t)c->nlines * c->nr * c->nth;
+  c->h_ld_src.assign(src, src + n);
+  c->h_ld_alp.assign(alp, alp + n);
+  c->have_line_dust = true;
+  c->have_dust = false;
+  return 0;
+}
+
+// telescope.F:715-1191 setup_rays_circular + 443-488 ring edges
+int rl_set_camera(rl_ctx *c, double anginf, int nphi, int nrext, int dbdr, double rstar, int imethod,
+                  int nrref) {
+  if (!c->nr) return fail(c, 13, "set_camera: call set_grid first");
+  cudaSetDevice(c->device);
+  const int nr = c->nr;
+  auto RC = [&](int i) { return c->rc[i + 1]; };
+  const double epsxyz = 1.0e2 * kTelescEps, epsrrr = 1.0e3 * kTelescEps;
+  if (imethod < 0) return fail(c, 1, "Negative imethod not allowed.");
+  int nrrextra = nrext < 0 ? -nrext : nrext;
+  if (imethod == 0) {
+    if (nrext > 0) imethod = -1;
+    else if (nrext < 0) imethod = -2;
+    else return fail(c, 1, "ERROR telescope.F: Must have non-zero nrrextra");
+  }
+  if (nphi < 1) return fail(c, 13, "nrphiinf must be positive");
+  if (nr <= 1) return fail(c, 13, "ERROR Telescope: irmax.le.irmin");
+  if (std::fabs(anginf) < 1.e-1) anginf = 0.1 * std::fabs(anginf) / anginf;  // telescope.F:818-827
+  const double theta0 = anginf + 1.e-4;
+  const double sinth0 = std::sin(theta0);
+  const double dphi = 6.28318530718 / (1.0 * nphi);
+  double phi = 0.5 * dphi;
+  std::vector<double> zhat0(nphi), xhat0(nphi);
+  for (int k = 0; k < nphi; k++) {
+    zhat0[k] = -std::sin(phi) / sinth0;
+    const double zh02 = zhat0[k] * zhat0[k];
+    double dum = 1.0 - zh02 * sinth0 * sinth0;
+    dum = dum + epsxyz;
+    if (dum >= 0.0) xhat0[k] = (std::cos(phi) > 0.0) ? std::sqrt(dum) : -std::sqrt(dum);
+    else return fail(c, 13, "ERROR in setup_rays_circular");
+    phi = phi + dphi;
+  }
+  std::vector<double> rings;  // rays_r(1..)
+  if (imethod < 0) {
+    for (int ix = 1; ix <= nrrextra; ix++) {
+      if (imethod == -2) {
+        if (rstar > RC(1)) return fail(c, 83991, "rstar larger than inner grid radius");
+        rings.push_back((ix * (RC(1) - rstar) / (nrrextra + 1.0)) + rstar);
+      } else {
+        rings.push_back(ix * RC(1) / (nrrextra + 1.0));
+      }
+    }
+  } else {
+    if (nrref <= 0) return fail(c, 1, "ERROR: If new method for ray-arrangement is chosen, then nrref must be set>0");
+    if (imethod != 1) return fail(c, 1, "ERROR: Do not know imethod as a method for arranging rays...");
+    double refdum1 = 0.5, refdum2 = 0.0;
+    for (int ix = 1; ix <= nrrextra + nrref; ix++) {
+      if (rstar > RC(1)) return fail(c, 91991, "rstar larger than inner grid radius");
+      if (ix <= nrrextra) {
+        rings.push_back(((ix - 1) * (RC(1) - rstar) / nrrextra) + rstar);
+      } else {
+        refdum2 = refdum2 + refdum1;
+        refdum1 = refdum1 / 2;
+        rings.push_back(((nrrextra + refdum2) * (RC(1) - rstar) / (nrrextra + 1.0)) + rstar);
+      }
+    }
+  }
+  for (int ix = 1; ix <= nr - 1; ix++) {
+    rings.push_back(RC(ix) * (1.0 + epsrrr));
+    if (dbdr > 1) {
+      const double dr = (RC(ix + 1) - RC(ix)) / (1.0 * dbdr);
+      for (int iins = 1; iins <= dbdr - 1; iins++) rings.push_back(RC(ix) + iins * dr);
+    }
+  }
+  const int nrr = (int)rings.size();
+  if ((long long)nrr * nphi + 1 > 2000000000LL) return fail(c, 13, "Exceeded maximum number of rays!!");
+  c->nrr = nrr;
+  c->nphi = nphi;
+  c->nray = 1 + nrr * nphi;
+  c->rays_r.assign(nrr + 1, 0.0);
+  for (int i = 0; i < nrr; i++) c->rays_r[i + 1] = rings[i];
+  c->rp_x0.assign(c->nray, 0.0);
+  c->rp_z0.assign(c->nray, 0.0);
+  for (int ir = 1; ir <= nrr; ir++)
+    for (int k = 0; k < nphi; k++) {
+      const size_t ray = 1 + (size_t)(ir - 1) * nphi + k;
+      c->rp_x0[ray] = rings[ir - 1] * xhat0[k];
+      c->rp_z0[ray] = rings[ir - 1] * zhat0[k];
+    }
+  // ring edges (telescope.F:443-488); nb == nrr for the layouts above
+  const int nb = nrr;
+  std::vector<double> &ri = c->imcir_ri;
+  ri.assign(nb + 2, 0.0);
+  for (int ir = 1; ir <= nb; ir++) ri[ir] = 0.5 * (c->rays_r[ir] + c->rays_r[ir - 1]);
+  ri[nb + 1] = RC(nr);
+  for (int ir = 1; ir <= nb - 1; ir++)
+    if (c->rays_r[ir] - ri[ir] > 2 * (ri[ir + 1] - c->rays_r[ir]))
+      ri[ir] = c->rays_r[ir] - 2 * (ri[ir + 1] - c->rays_r[ir]);
+  if (ri[1] < rstar) {
+    if (c->rays_r[1] < rstar) return fail(c, 1, "INTERNAL ERROR IN RAY-SETUP...");
+    ri[1] = rstar;
+  }
+  // ring areas of telescope.F:1393, 1409 (rapert = 1d99)
+  c->surf.assign(nrr + 1, 0.0);
+  c->surf[0] = 3.14159265359 * (ri[1] * ri[1]);
+  for (int ir = 1; ir <= nrr; ir++) c->surf[ir] = 3.14159265359 * (ri[ir + 1] * ri[ir + 1] - ri[ir] * ri[ir]);
+  c->anginf = anginf;
+  c->theta0 = theta0;
+  c->rstar = rstar;
+  c->nrext = nrext;
+  c->dbdr = dbdr;
+  c->imethod = imethod;
+  c->nrref = nrref;
+  CU(c->d_x0.upload(c->rp_x0, c->st));
+  CU(c->d_z0.upload(c->rp_z0, c->st));
+  CU(c->d_surf.upload(c->surf, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->cam_set = true;
+  c->geom_valid = false;
+  c->cmask_accum_n = 0;
+  return 0;
+}
+
+int rl_set_bc(rl_ctx *c, int in_itype, int out_itype, int ncf, const double *cont_freq_nu,
+              const double *starspec_cont, const double *isrf_cont) {
+  c->in_itype = in_itype;
+  c->out_itype = out_itype;
+  c->cfreq_b.assign(cont_freq_nu, cont_freq_nu + ncf);
+  c->starspec_cont.assign(starspec_cont, starspec_cont + ncf);
+  if (isrf_cont) c->isrf_cont.assign(isrf_cont, isrf_cont + ncf);
+  else c->isrf_cont.clear();
+  c->bc_set = true;
+  c->geom_valid = false;  // node flags depend on the inner BC type
+  return 0;
+}
+
+int rl_set_options(rl_ctx *c, int subgrid, int nonredundant, double levthres, double aksmax) {
+  c->subgrid = subgrid;
+  c->nonredundant = nonredundant;
+  c->levthres = levthres;
+  c->aksmax_opt = aksmax;
+  return 0;
+}
+
+int rl_get_camera_dims(rl_ctx *c, int *nrr, int *nphi, int *nray) {
+  if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
+  if (nrr) *nrr = c->nrr;
+  if (nphi) *nphi = c->nphi;
+  if (nray) *nray = c->nray;
+  return 0;
+}
+
+int rl_get_rings(rl_ctx *c, double *rays_r, double *imcir_ri) {
+  if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
+  std::copy(c->rays_r.begin(), c->rays_r.end(), rays_r);
+  std::copy(c->imcir_ri.begin(), c->imcir_ri.end(), imcir_ri);
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- geometry ---------------------------------------------------------------------------------
+static int check_status(rl_ctx *c, const char *where) {
+  int st = 0;
+  CU(cudaMemcpyAsync(&st, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  if (st != 0) {
+    const char *msg = "device-side consistency check failed";
+    switch (st) {
+      case 6024: msg = "ERROR: Erroneous dr found"; break;
+      case 6023: msg = "ERROR: Erroneous dt found"; break;
+      case 749: msg = "charintline: ds<0"; break;
+      case 393: msg = "omega_dot_v: mu>1"; break;
+      case 124: msg = "PROBLEM: The central beam of the circular CCD has a size smaller than the stellar radius"; break;
+      case 192: msg = "telescope.F/make_traject_t(): hunt failed"; break;
+      case 13: msg = "trajectory / boundary condition error (stop 13)"; break;
+      case 9001: msg = "internal: theta-cone hit set not contiguous"; break;
+    }
+    char b[256];
+    snprintf(b, sizeof b, "%s (%s)", msg, where);
+    return fail(c, st, b);
+  }
+  return 0;
+}
+
+static GridDev grid_dev(rl_ctx *c) {
+  GridDev g;
+  g.nr = c->nr;
+  g.nt = c->nt;
+  g.nth = c->nth;
+  g.rc = c->d_rc.p;
+  g.tc = c->d_tc.p;
+  g.ridx = c->d_ridx.p;
+  return g;
+}
+
+static NodesDev nodes_dev(rl_ctx *c) {
+  NodesDev n;
+  n.ds = c->d_nds.p;
+  n.dvmu = c->d_ndvmu.p;
+  n.lw = c->d_nlw.p;
+  n.wr = c->d_nwr.p;
+  n.wt = c->d_nwt.p;
+  n.cell = c->d_ncell.p;
+  n.flag = c->d_nflag.p;
+  return n;
+}
+
+static int ensure_geometry(rl_ctx *c) {
+  if (c->geom_valid) return 0;
+  // telescope.F:4323-4340 telescope_check_safety_numbers
+  for (int ir = 1; ir <= c->nr - 1; ir++)
+    if (c->rc[ir + 2] / c->rc[ir + 1] - 1.0 < 1.e4 * kTelescEps)
+      return fail(c, 13, "PROBLEM in telescope: The radial grid resolution is too fine for TELESC_EPS");
+  GeomParams P;
+  P.g = grid_dev(c);
+  P.nray = c->nray;
+  P.x0 = c->d_x0.p;
+  P.z0 = c->d_z0.p;
+  P.theta0 = c->theta0;
+  P.rstar = c->rstar;
+  P.in_itype = c->in_itype;
+  P.rbeam0_center = c->imcir_ri[1];
+  P.cellS = c->d_cellS.p;
+  P.status = c->d_status.p;
+  CU(c->d_node_cnt.ensure(c->nray));
+  CU(c->d_node_off.ensure((size_t)c->nray + 1));
+  CU(cudaMemsetAsync(c->d_status.p, 0, sizeof(int), c->st));
+  P.node_cnt = c->d_node_cnt.p;
+  P.node_off = nullptr;
+  P.nodes = NodesDev{};
+  launch_geom(P, true, c->st);
+  c->launches++;
+  CU(cudaGetLastError());
+  std::vector<int> cnt(c->nray);
+  CU(cudaMemcpyAsync(cnt.data(), c->d_node_cnt.p, sizeof(int) * c->nray, cudaMemcpyDeviceToHost, c->st));
+  int rcode = check_status(c, "ray geometry, count pass");
+  if (rcode) return rcode;
+  c->h_node_off.assign((size_t)c->nray + 1, 0);
+  c->max_nodes = 0;
+  for (int i = 0; i < c->nray; i++) {
+    c->h_node_off[i + 1] = c->h_node_off[i] + cnt[i];
+    c->max_nodes = std::max(c->max_nodes, cnt[i]);
+  }
+  c->total_nodes = c->h_node_off[c->nray];
+  CU(c->d_node_off.upload(c->h_node_off, c->st));
+  const size_t n = (size_t)c->total_nodes;
+  CU(c->d_nds.ensure(n));
+  CU(c->d_ndvmu.ensure(n));
+  CU(c->d_nlw.ensure(n));
+  CU(c->d_nwr.ensure(n));
+  CU(c->d_nwt.ensure(n));
+  CU(c->d_ncell.ensure(n));
+  CU(c->d_nflag.ensure(n));
+  P.node_off = c->d_node_off.p;
+  P.nodes = nodes_dev(c);
+  launch_geom(P, false, c->st);
+  c->launches++;
+  CU(cudaGetLastError());
+  rcode = check_status(c, "ray geometry, fill pass");
+  if (rcode) return rcode;
+  c->geom_valid = true;
+  return 0;
+}
+
+// ---- render -----------------------------------------------------------------------------------
+static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
+                       double *flux, double *imcir, int *cmask, double *tau_center, int *maserflag,
+                       double *velo_out, float *kernel_ms, bool device_only) {
+  // telescope.F:366-370, 1511-1515 readiness checks
+  if (!c->nr || !c->have_medium || !c->nlines || !(c->have_dust || c->have_line_dust) || !c->cam_set ||
+      !c->bc_set)
+    return fail(c, 13, "ERROR, make_image_circular(): Ray paramters not yet set (grid/medium/lines/dust/camera/bc)");
+  if (iline0 < 1 || nl < 1 || iline0 + nl - 1 > c->nlines) return fail(c, 13, "render: line range out of bounds");
+  if (nfr < 1) return fail(c, 13, "Number of frequencies for this line is out of range");
+  if (nfr == 1) return fail(c, 13, "ERROR: Simple square line profile deactivated");
+  if (c->bc_set && c->cfreq_b.empty())
+    return fail(c, 1, "ERROR: Cannot use line stellar BC without having read the stellar spectrum.");
+  if (c->out_itype == 1) return fail(c, 13, "Outer BC type 1 not allowed for telescope");
+  if (c->out_itype != 0 && c->out_itype != 2 && c->out_itype != 3)
+    return fail(c, 13, "Telecope: dont know this type of outer BC");
+  if (c->out_itype == 3 && c->isrf_cont.empty())
+    return fail(c, 1, "ERROR: Cannot use line outer BC without having read the interstellar spectrum.");
+  cudaSetDevice(c->device);
+  float ms_acc[4] = {0, 0, 0, 0};
+  CU(cudaEventRecord(c->ev[0], c->st));
+  int rcode = ensure_geometry(c);
+  if (rcode) return rcode;
+  CU(cudaEventRecord(c->ev[1], c->st));
+  CU(cudaEventSynchronize(c->ev[1]));
+  CU(cudaEventElapsedTime(&ms_acc[0], c->ev[0], c->ev[1]));
+
+  const size_t ncell = (size_t)c->nr * c->nth;
+  const size_t nrow = (size_t)(c->nrr + 1) * c->nphi;
+  const bool want_mask = cmask != nullptr;
+  // aksmax: line.F:2982-3033 (global max of locprof_linewidth)
+  double aksmax = c->aksmax_opt;
+  if (aksmax < 0.0) {
+    aksmax = 0.0;
+    for (double v : c->h_lw)
+      if (v > aksmax) aksmax = v;
+  }
+  // lines per batch: image buffer <= ~6 GiB and item count < 2^32
+  const double per_line_bytes = (double)nrow * nfr * 8.0 + (double)ncell * 32.0;
+  int lb = (int)std::max(1.0, std::floor(6.0 * 1073741824.0 / per_line_bytes));
+  lb = (int)std::min<double>(lb, std::floor(4.0e9 / ((double)c->nray * nfr)));
+  lb = std::max(1, std::min(lb, nl));
+  if (want_mask) {
+    const long long per = (long long)nrow * nfr;
+    if (c->cmask_accum_n != per) {
+      CU(c->d_cmask_accum.ensure(per));
+      CU(cudaMemsetAsync(c->d_cmask_accum.p, 0, per, c->st));
+      c->cmask_accum_n = per;
+    }
+  }
+  c->last_flux.assign((size_t)nl * nfr, 0.0);
+  c->last_nl = nl;
+  c->last_nfr = nfr;
+
+  for (int b0 = 0; b0 < nl; b0 += lb) {
+    const int nb = std::min(lb, nl - b0);
+    // ---- host tables per line: passband, star / outer BC, B's, dust bracket ----
+    std::vector<LineDev> lines(nb);
+    std::vector<double> line_dnu((size_t)nb * nfr), velo((size_t)nb * nfr), star((size_t)nb * nfr),
+        isrf((size_t)nb * nfr, 0.0), wgt(nb, 0.0), freq(nb, 0.0);
+    std::vector<int> lup(nb), ldn(nb), inud(nb, 0);
+    for (int l = 0; l < nb; l++) {
+      const int il = iline0 - 1 + b0 + l;
+      const double nu0 = std::fabs(c->linefreq[il]);
+      if (nu0 == 0.0) return fail(c, 13, "Problem in line_setup_passband(): nu0=0 !");
+      // line.F:462-469
+      const double passb = 3.33567e-6 * nu0 * vmax_kms;
+      const double nu1 = 0.0 - passb;
+      const double dnu = 2.0 * passb / (nfr - 1.0);
+      LineDev &L = lines[l];
+      L.nu0 = c->linefreq[il];
+      L.aud = c->aud[il];
+      L.bud = c->bud[il];
+      L.bdu = c->bdu[il];
+      L.dnu0 = nu1;
+      L.ddnu = dnu;
+      L.i_outer = 0.0;
+      if (c->out_itype == 2) {  // telescope.F:3996-4000
+        const double f = c->linefreq[il];
+        L.i_outer = 1.47455253991e-47 * (f * f * f) / (std::exp(4.7991598e-11 * f / kTempCmb) - 1.0);
+      }
+      const int ncf = (int)c->cfreq_b.size();
+      const double *cf = c->cfreq_b.data();
+      for (int k = 1; k <= nfr; k++) {
+        const double d = nu1 + (k - 1) * dnu;
+        const double fr = nu0 + d;
+        line_dnu[(size_t)l * nfr + k - 1] = d;
+        velo[(size_t)l * nfr + k - 1] = d / c->linefreq[il];
+        const int j = hunt_host(cf, ncf, fr);  // line.F:3835-3846
+        double sv = 0.0;
+        if (!(j == 0 || j == ncf)) {
+          const double w = (fr - cf[j - 1]) / (cf[j] - cf[j - 1]);
+          sv = (1.0 - w) * c->starspec_cont[j - 1] + w * c->starspec_cont[j];
+        }
+        star[(size_t)l * nfr + k - 1] = sv;
+        if (c->out_itype == 3) {  // line.F:3888-3900 (compares with freq_nr = nfr, sic)
+          double iv = 0.0;
+          if (!(j == 0 || j == nfr)) {
+            const double w = (fr - cf[j - 1]) / (cf[j] - cf[j - 1]);
+            iv = (1.0 - w) * c->isrf_cont[j - 1] + w * c->isrf_cont[j];
+          }
+          isrf[(size_t)l * nfr + k - 1] = iv;
+        }
+      }
+      lup[l] = c->lev_up[il];
+      ldn[l] = c->lev_down[il];
+      if (c->have_dust) {  // line.F:3560-3574
+        const double f = c->linefreq[il];
+        const int j = hunt_host(c->cfreq_d.data(), c->ncf_d, f);
+        inud[l] = j;
+        freq[l] = f;
+        if (!(j == 0 || j == c->ncf_d)) wgt[l] = (f - c->cfreq_d[j - 1]) / (c->cfreq_d[j] - c->cfreq_d[j - 1]);
+      }
+    }
+    CU(c->d_lines.upload(lines, c->st));
+    CU(c->d_line_dnu.upload(line_dnu, c->st));
+    CU(c->d_velo.upload(velo, c->st));
+    CU(c->d_star_line.upload(star, c->st));
+    CU(c->d_isrf_line.upload(isrf, c->st));
+    CU(c->d_lev_up.upload(lup, c->st));
+    CU(c->d_lev_down.upload(ldn, c->st));
+    CU(c->d_inudust.upload(inud, c->st));
+    CU(c->d_wgt.upload(wgt, c->st));
+    CU(c->d_freq.upload(freq, c->st));
+    if (!c->have_dust) {
+      const size_t off = (size_t)(iline0 - 1 + b0) * ncell;
+      CU(c->d_ld_src.upload(c->h_ld_src.data() + off, (size_t)nb * ncell, c->st));
+      CU(c->d_ld_alp.upload(c->h_ld_alp.data() + off, (size_t)nb * ncell, c->st));
+    }
+    const size_t ntask = (size_t)nb * c->nray;
+    CU(c->d_cellL.ensure((size_t)nb * ncell));
+    CU(c->d_rng.ensure(ntask));
+    CU(c->d_nitems.ensure(ntask + 1));
+    CU(c->d_item_off.ensure(ntask + 1));
+    CU(c->d_img.ensure((size_t)nb * nrow * nfr));
+    CU(c->d_ring.ensure((size_t)nb * c->nrr * nfr));
+    CU(c->d_flux.ensure((size_t)nl * nfr));
+    CU(c->d_tau.ensure(nb));
+    CU(c->d_maser.ensure(nb));
+    if (want_mask) {
+      CU(c->d_integ.ensure((size_t)nb * nrow * nfr));
+      CU(cudaMemsetAsync(c->d_integ.p, 0, (size_t)nb * nrow * nfr, c->st));
+      CU(c->d_cmask_out.ensure((size_t)nb * nrow * nfr));
+    }
+    CU(cudaMemsetAsync(c->d_maser.p, 0, sizeof(int) * nb, c->st));
+    CU(cudaMemsetAsync(c->d_tau.p, 0, sizeof(double) * nb, c->st));
+    CU(cudaMemsetAsync(c->d_status.p, 0, sizeof(int), c->st));
+    CU(cudaMemsetAsync(c->d_nitems.p + ntask, 0, sizeof(unsigned), c->st));
+
+    // ---- per-line preparation ----
+    CU(cudaEventRecord(c->ev[1], c->st));
+    PrepParams Q;
+    Q.ncell = (long long)ncell;
+    Q.nl = nb;
+    Q.nlevels = c->nlevels;
+    Q.popul = c->d_popul.p;
+    Q.abund = c->d_abund.p;
+    Q.rho = c->d_rho.p;
+    Q.molpg = 1.0 / (c->umass_av * 1.6726e-24);  // line.F:3998
+    Q.lev_up = c->d_lev_up.p;
+    Q.lev_down = c->d_lev_down.p;
+    Q.use_dust = c->have_dust ? 1 : 0;
+    Q.nspec = c->nspec;
+    Q.maxsize = c->maxsize;
+    Q.ncf = c->ncf_d;
+    Q.nsize = c->d_nsize.p;
+    Q.kabs = c->d_kabs.p;
+    Q.kscat = c->d_kscat.p;
+    Q.drho = c->d_drho.p;
+    Q.dtemp = c->d_dtemp.p;
+    Q.scat = c->have_scat ? c->d_scat.p : nullptr;
+    Q.inudust = c->d_inudust.p;
+    Q.wgt = c->d_wgt.p;
+    Q.freq = c->d_freq.p;
+    Q.ld_src = c->d_ld_src.p;
+    Q.ld_alp = c->d_ld_alp.p;
+    Q.cellL = c->d_cellL.p;
+    launch_prep(Q, c->st);
+    c->launches++;
+
+    RenderParams P;
+    P.g = grid_dev(c);
+    P.nray = c->nray;
+    P.nphi = c->nphi;
+    P.nrr = c->nrr;
+    P.nl = nb;
+    P.nfr = nfr;
+    P.subgrid = c->subgrid;
+    P.nonredundant = c->nonredundant;
+    P.levthres = c->levthres;
+    P.aksmax_c = aksmax / 2.99792458e5;
+    {
+      const double rb = c->imcir_ri[1];
+      P.starfract = (c->rstar / rb) * (c->rstar / rb);
+    }
+    P.out_itype = c->out_itype;
+    P.node_off = c->d_node_off.p;
+    P.nodes = nodes_dev(c);
+    P.cellL = c->d_cellL.p;
+    P.ncell = (long long)ncell;
+    P.lines = c->d_lines.p;
+    P.line_dnu = c->d_line_dnu.p;
+    P.velo = c->d_velo.p;
+    P.star_line = c->d_star_line.p;
+    P.isrf_line = c->d_isrf_line.p;
+    P.rng = c->d_rng.p;
+    P.nitems = c->d_nitems.p;
+    P.item_off = c->d_item_off.p;
+    P.img = c->d_img.p;
+    P.integ = want_mask ? c->d_integ.p : nullptr;
+    P.tau_center = c->d_tau.p;
+    P.maser = c->d_maser.p;
+    P.counters = c->d_counters.p;
+    P.status = c->d_status.p;
+    launch_span(P, c->st);
+    c->launches++;
+    {
+      size_t tmp_bytes = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_nitems.p, c->d_item_off.p, (int)(ntask + 1), c->st);
+      CU(c->d_scan_tmp.ensure(tmp_bytes));
+      CU(cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, c->d_nitems.p, c->d_item_off.p,
+                                       (int)(ntask + 1), c->st));
+      c->launches++;
+    }
+    unsigned total_items = 0;
+    CU(cudaMemcpyAsync(&total_items, c->d_item_off.p + ntask, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaEventRecord(c->ev[2], c->st));
+    CU(cudaStreamSynchronize(c->st));
+    // ---- ray integration ----
+    launch_integrate(P, total_items, c->st);
+    CU(cudaEventRecord(c->ev[5], c->st));
+    launch_fill(P, c->st);
+    c->launches += 2;
+    if (imcir) {
+      launch_center_replicate(P, c->st);
+      c->launches++;
+    }
+    CU(cudaEventRecord(c->ev[3], c->st));
+    // ---- flux ----
+    launch_flux(P, c->d_surf.p, c->d_ring.p, dist_cm * dist_cm, c->d_flux.p + (size_t)b0 * nfr, c->st);
+    c->launches += 2;
+    if (want_mask) {
+      launch_cmask(P, c->d_cmask_accum.p, c->d_cmask_out.p, c->st);
+      c->launches++;
+    }
+    CU(cudaEventRecord(c->ev[4], c->st));
+    CU(cudaGetLastError());
+    // ---- results back ----
+    if (!device_only) {
+      if (imcir)
+        CU(cudaMemcpyAsync(imcir + (size_t)b0 * nrow * nfr, c->d_img.p, (size_t)nb * nrow * nfr * sizeof(double),
+                           cudaMemcpyDeviceToHost, c->st));
+      if (want_mask)
+        CU(cudaMemcpyAsync(cmask + (size_t)b0 * nrow * nfr, c->d_cmask_out.p,
+                           (size_t)nb * nrow * nfr * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+      if (tau_center)
+        CU(cudaMemcpyAsync(tau_center + b0, c->d_tau.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->st));
+      if (maserflag)
+        CU(cudaMemcpyAsync(maserflag + b0, c->d_maser.p, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->st));
+      if (velo_out) std::copy(velo.begin(), velo.end(), velo_out + (size_t)b0 * nfr);
+    }
+    rcode = check_status(c, "ray integration");
+    if (rcode) return rcode;
+    float ms;
+    CU(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
+    ms_acc[1] += ms;
+    CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[5]));
+    ms_acc[2] += ms;
+    CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[4]));
+    ms_acc[3] += ms;
+  }
+  if (!device_only && flux) {
+    CU(cudaMemcpyAsync(flux, c->d_flux.p, (size_t)nl * nfr * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+  }
+  if (kernel_ms) {
+    for (int i = 0; i < 4; i++) kernel_ms[i] = ms_acc[i];
+    CU(cudaEventRecord(c->ev[1], c->st));
+    CU(cudaEventSynchronize(c->ev[1]));
+    CU(cudaEventElapsedTime(&kernel_ms[4], c->ev[0], c->ev[1]));
+  }
+  return 0;
+}
+
+extern "C" {
+
+int rl_render(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm, double *flux,
+              double *imcir, int *cmask, double *tau_center, int *maserflag, double *velo) {
+  if (!flux) return fail(c, 13, "render: flux pointer is required");
+  return render_impl(c, iline0, nl, nfr, vmax_kms, dist_cm, flux, imcir, cmask, tau_center, maserflag, velo,
+                     nullptr, false);
+}
+
+int rl_render_device(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
+                     float *kernel_ms) {
+  return render_impl(c, iline0, nl, nfr, vmax_kms, dist_cm, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, kernel_ms, true);
+}
+
+int rl_fetch_flux(rl_ctx *c, int nl, int nfr, double *flux) {
+  if (nl != c->last_nl || nfr != c->last_nfr) return fail(c, 13, "fetch_flux: shape differs from the last render");
+  cudaSetDevice(c->device);
+  CU(cudaMemcpyAsync(flux, c->d_flux.p, (size_t)nl * nfr * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+void rl_get_counters(const rl_ctx *cc, double *R, double *E, double *S) {
+  rl_ctx *c = const_cast<rl_ctx *>(cc);
+  unsigned long long h[3] = {0, 0, 0};
+  cudaSetDevice(c->device);
+  cudaMemcpyAsync(h, c->d_counters.p, sizeof h, cudaMemcpyDeviceToHost, c->st);
+  cudaStreamSynchronize(c->st);
+  if (R) *R = (double)h[0];
+  if (E) *E = (double)h[1];
+  if (S) *S = (double)h[2];
+}
+
+void rl_reset_counters(rl_ctx *c) {
+  cudaSetDevice(c->device);
+  cudaMemsetAsync(c->d_counters.p, 0, 3 * sizeof(unsigned long long), c->st);
+  cudaStreamSynchronize(c->st);
+}
+
+long long rl_launch_count(const rl_ctx *c) { return c->launches; }
+void rl_invalidate_geometry(rl_ctx *c) { c->geom_valid = false; }
+
+int rl_fp64_peak(rl_ctx *c, double *tflops) {
+  cudaSetDevice(c->device);
+  DevBuf<double> sink;
+  CU(sink.ensure(1 << 20));
+  const int blocks = 148 * 8, threads = 256, iters = 4096;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(c->ev[0], c->st));
+    launch_dfma_peak(sink.p, iters, blocks, threads, c->st);
+    c->launches++;
+    CU(cudaEventRecord(c->ev[1], c->st));
+    CU(cudaEventSynchronize(c->ev[1]));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  // 16 independent chains x 2 flop per DFMA per iteration per thread
+  const double flop = (double)blocks * threads * (double)iters * 16.0 * 2.0;
+  *tflops = flop / (best * 1e-3) / 1e12;
+  return 0;
+}
+int rl_max_nodes(const rl_ctx *c) { return c->max_nodes; }
+long long rl_total_nodes(const rl_ctx *c) { return c->total_nodes; }
+
+int rl_get_ray_nodes(rl_ctx *c, int iray, double *ds, double *dvmu, double *lw, double *wr, double *wt,
+                     int *cells4, int *flags) {
+  if (!c->nr || !c->have_medium || !c->cam_set || !c->bc_set) {
+    fail(c, 13, "get_ray_nodes: model incomplete");
+    return -13;
+  }
+  cudaSetDevice(c->device);
+  int rcode = ensure_geometry(c);
+  if (rcode) return -std::abs(rcode);
+  if (iray < 1 || iray > c->nray) return -13;
+  const long long n0 = c->h_node_off[iray - 1], n = c->h_node_off[iray] - n0;
+  auto cp = [&](void *dst, const void *src, size_t bytes) {
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->st);
+  };
+  if (ds) cp(ds, c->d_nds.p + n0, n * 8);
+  if (dvmu) cp(dvmu, c->d_ndvmu.p + n0, n * 8);
+  if (lw) cp(lw, c->d_nlw.p + n0, n * 8);
+  if (wr) cp(wr, c->d_nwr.p + n0, n * 8);
+  if (wt) cp(wt, c->d_nwt.p + n0, n * 8);
+  if (cells4) cp(cells4, c->d_ncell.p + n0, n * 16);
+  if (flags) cp(flags, c->d_nflag.p + n0, n * 4);
+  cudaStreamSynchronize(c->st);
+  return (int)n;
+}
+
+}  // extern "C"

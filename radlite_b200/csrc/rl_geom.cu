@@ -1,0 +1,471 @@
+// rl_geom.cu -- ray geometry on the device: one thread per camera ray builds the ray's node list
+// (crossings with the R and Theta grid surfaces plus the extremum sampling points), the
+// interpolation stencil of every node and the line-independent node quantities
+// (segment length, projected velocity Omega.v/c, line width).  Built once per camera/grid and
+// reused by every line and channel.
+//
+// Follows telescope.F:2787-3720 (make_trajectory_c) and the node bookkeeping of
+// telescope.F:3948-3958, 4046-4104, 4148-4193 (charintline) and line.F:3986-4039, 4090-4094,
+// 2650-2662 (stencil, velocity interpolation, omega_dot_v).  Unlike the reference nothing is
+// materialised per surface: the three crossing families are generated as sorted streams and merged
+// on the fly, so a ray needs O(1) scratch.
+//
+// Compile this file with --fmad=false: the guards (1e-10 discriminant pad, 1e-9 radius windows,
+// hunt brackets) are meant to see the same rounding as the reference's separate mul/add.
+#include "rl_types.h"
+
+#include <math.h>
+
+namespace rl {
+
+namespace {
+
+__device__ __forceinline__ double RCf(const GridDev &g, int i) { return g.rc[i + 1]; }
+__device__ __forceinline__ double TCf(const GridDev &g, int i) { return g.tc[i + 1]; }
+__device__ __forceinline__ int RIDXf(const GridDev &g, int i) { return g.ridx[i + 4]; }
+
+// nrecip.F:157 hunt, bisection phase from (0, n+1): largest j in 0..n with xx(j) < x.
+// xx1 points at xx(1).
+__device__ int hunt_bisect(const double *xx1, int n, double x) {
+  int jlo = 0, jhi = n + 1;
+  while (jhi - jlo != 1) {
+    int jm = (jhi + jlo) >> 1;
+    if (x > xx1[jm - 1]) jlo = jm;
+    else jhi = jm;
+  }
+  return jlo;
+}
+
+struct Ray {
+  GridDev g;
+  double x0, z0, costh0, sinth0, costh02, sinth02, pitheta0;
+  // theta-crossing stream
+  int isnr, isdbl, iy_first, iup, branchA, ith_amount;
+  // R-crossing stream
+  int ir_min, ir_amount;
+  double rstar;
+};
+
+// both roots of the theta=const cone iy (telescope.F:2960-2990), ordered sar1 <= sar2
+__device__ bool th_roots(const Ray &R, int iy, double &sar1, double &sar2) {
+  double theta = TCf(R.g, iy);
+  double t = tan(theta);
+  double tanth2 = t * t;
+  double a = tanth2 * R.costh02 - R.sinth02;
+  double b = 2.0 * tanth2 * R.costh0 * R.z0;
+  double c = tanth2 * R.z0 * R.z0 - R.x0 * R.x0;
+  double sdiscr = b * b - 4.0 * a * c;
+  if (!(sdiscr > 0.0)) return false;
+  sdiscr = sqrt(sdiscr);
+  sar1 = (-b - sdiscr) / (2.0 * a);
+  sar2 = (-b + sdiscr) / (2.0 * a);
+  if (sar1 > sar2) {
+    double d = sar1;
+    sar1 = sar2;
+    sar2 = d;
+  }
+  return true;
+}
+
+// k-th theta crossing along the ray, k = 1..ith_amount (telescope.F:3024-3194 ordering)
+__device__ void th_elem(const Ray &R, int k, double &s, int &itheta) {
+  const int n = R.isnr, d = R.isdbl;
+  int is, which, pat;  // which: 0 = sar1, 1 = sar2 ; pat 1: iup ? nt+1-iy : iy ; pat 2: iup ? iy : nt+1-iy
+  if (R.branchA) {
+    if (k <= n - d) { is = d + k; which = 0; pat = 1; }
+    else if (k <= 2 * n - 2 * d) { is = n - (k - (n - d + 1)); which = 1; pat = 2; }
+    else if (k <= 2 * n - d) { is = d - (k - (2 * n - 2 * d + 1)); which = 0; pat = 2; }
+    else { is = 1 + (k - (2 * n - d + 1)); which = 1; pat = 2; }
+  } else {
+    if (k <= d) { is = d - (k - 1); which = 0; pat = 1; }
+    else if (k <= 2 * d) { is = k - d; which = 1; pat = 1; }
+    else if (k <= n + d) { is = d + 1 + (k - (2 * d + 1)); which = 0; pat = 1; }
+    else { is = n - (k - (n + d + 1)); which = 1; pat = 2; }
+  }
+  int iy = R.iy_first + is - 1;
+  double a1 = 0.0, a2 = 0.0;
+  th_roots(R, iy, a1, a2);
+  s = which ? a2 : a1;
+  bool mirrored = (pat == 1) ? (R.iup == 1) : (R.iup != 1);
+  itheta = mirrored ? (R.g.nt + 1 - iy) : iy;
+}
+__device__ double th_s_at(const Ray &R, int k) {
+  if (k > R.ith_amount) return 1.e30;
+  double s;
+  int it;
+  th_elem(R, k, s, it);
+  return s;
+}
+
+// k-th R crossing, k = 1..ir_amount (telescope.F:3284-3335)
+__device__ void r_elem(const Ray &R, int k, double &s, int &ix, double &r) {
+  int j = (k <= R.ir_amount / 2) ? k : (R.ir_amount + 1 - k);
+  ix = R.g.nr - (j - 1);
+  r = (ix == 0) ? R.rstar : RCf(R.g, ix);
+  double b = 2.0 * R.costh0 * R.z0;
+  double c = R.x0 * R.x0 + R.z0 * R.z0 - r * r;
+  double sdiscr = b * b - 4.0 * 1.0 * c + kTelescEps * b * b;
+  sdiscr = sqrt(sdiscr);  // sdiscr<0 cannot occur for ix>=ir_min (reference: stop 13)
+  s = (k <= R.ir_amount / 2) ? (-b - sdiscr) / (2.0 * 1.0) : (-b + sdiscr) / (2.0 * 1.0);
+}
+__device__ double r_s_at(const Ray &R, int k) {
+  if (k <= 0) return 0.0;  // r_s(0): read uninitialised by the reference for the outer ring; 0 by convention
+  if (k > R.ir_amount) return 1.e30;
+  double s, r;
+  int ix;
+  r_elem(R, k, s, ix, r);
+  return s;
+}
+
+__device__ double theta_of_s(const Ray &R, double s) {
+  double th = atan(sqrt(R.x0 * R.x0 + R.sinth02 * s * s) / (R.z0 + R.costh0 * s));
+  if (th < 0.0) th = th + kPi;
+  return th;
+}
+__device__ double radius_of_s(const Ray &R, double s) {
+  return sqrt(R.x0 * R.x0 + R.z0 * R.z0 + s * s + 2.0 * R.z0 * R.costh0 * s);
+}
+
+struct Extra {
+  double s, radius, theta;
+  int ir, it;
+};
+
+struct Emit {
+  // running state of charintline's node loop
+  int n;
+  int ir_old, icr_old;
+  double s_prev;
+  int star_done;
+};
+
+template <bool COUNT>
+__device__ void emit_node(const GeomParams &P, const Ray &R, Emit &E, long long base, int iray,
+                          int icr, double radius, double theta, int ir, int it, double s,
+                          double znew, double bnew) {
+  if (COUNT) {
+    E.n++;
+    return;
+  }
+  const GridDev &g = P.g;
+  const long long idx = base + E.n;
+  // local direction (telescope.F:3692-3718)
+  double snew = s + R.z0 * R.costh0;
+  double mu = snew / sqrt(bnew * bnew + snew * snew);
+  double dummy = bnew * sqrt(bnew * bnew + snew * snew - (znew + snew * R.costh0) * (znew + snew * R.costh0));
+  double sinphi;
+  if (dummy > 0.0) sinphi = (bnew * bnew * R.costh0 - znew * snew) / dummy;
+  else sinphi = 1.e1 * kTelescEps;
+  double phi = (R.x0 < 0.0) ? asin(sinphi) : (kPi - asin(sinphi));
+  while (phi < 0.0) phi = phi + 2.0 * kPi;
+  while (phi >= 2.0 * kPi) phi = phi - 2.0 * kPi;
+  // position inside the cell (telescope.F:3955-3958, 4088-4091)
+  double dr = (radius - RCf(g, ir)) / (RCf(g, ir + 1) - RCf(g, ir));
+  double dt = (theta - TCf(g, it)) / (TCf(g, it + 1) - TCf(g, it));
+  if (dr < 0.0 || dr > 1.0) atomicCAS(P.status, 0, 6024);
+  if (dt < 0.0 || dt > 1.0) atomicCAS(P.status, 0, 6023);
+  // stencil (line.F:4006-4039)
+  int r0 = ir, r1, t0 = it, t1;
+  if (dr > 0.0) { r1 = ir + 1; if (r1 > g.nr) r1 = g.nr; }
+  else { r1 = ir - 1; if (r1 < 1) r1 = 1; }
+  t1 = (dt > 0.0) ? it + 1 : it - 1;
+  t0 = RIDXf(g, t0);
+  t1 = RIDXf(g, t1);
+  r0 = max(1, min(g.nr, r0));  // (memory safety only; ir is in 1..nr for accepted nodes)
+  int4 cells;
+  cells.x = (r0 - 1) * g.nth + (t0 - 1);
+  cells.y = (r0 - 1) * g.nth + (t1 - 1);
+  cells.z = (r1 - 1) * g.nth + (t0 - 1);
+  cells.w = (r1 - 1) * g.nth + (t1 - 1);
+  // line width and velocity (line.F:4065-4067, 4090-4094 and the icr=2,3 twins)
+  double lw, v1, v2, v3;
+  {
+    double4 a = P.cellS[cells.x];
+    if (icr == 1) {
+      double4 b = P.cellS[cells.y];
+      lw = (1.0 - dt) * a.x + dt * b.x;
+      v1 = (1.0 - dt) * a.y + dt * b.y;
+      v2 = (1.0 - dt) * a.z + dt * b.z;
+      v3 = (1.0 - dt) * a.w + dt * b.w;
+    } else if (icr == 2) {
+      double4 b = P.cellS[cells.z];
+      lw = (1.0 - dr) * a.x + dr * b.x;
+      v1 = (1.0 - dr) * a.y + dr * b.y;
+      v2 = (1.0 - dr) * a.z + dr * b.z;
+      v3 = (1.0 - dr) * a.w + dr * b.w;
+    } else {
+      double4 b = P.cellS[cells.y], c = P.cellS[cells.z], d = P.cellS[cells.w];
+      lw = (1.0 - dr) * ((1.0 - dt) * a.x + dt * b.x) + dr * ((1.0 - dt) * c.x + dt * d.x);
+      v1 = (1.0 - dr) * ((1.0 - dt) * a.y + dt * b.y) + dr * ((1.0 - dt) * c.y + dt * d.y);
+      v2 = (1.0 - dr) * ((1.0 - dt) * a.z + dt * b.z) + dr * ((1.0 - dt) * c.z + dt * d.z);
+      v3 = (1.0 - dr) * ((1.0 - dt) * a.w + dt * b.w) + dr * ((1.0 - dt) * c.w + dt * d.w);
+    }
+  }
+  if (mu > 1.0) atomicCAS(P.status, 0, 393);  // line.F:2656
+  double dvmu = 3.335668e-11 * (mu * v1 + sqrt(1.0 - mu * mu) * (v2 * sin(phi) + v3 * cos(phi)));
+  // segment bookkeeping (telescope.F:4050-4104, 4129-4193)
+  uint32_t flag = (uint32_t)icr;
+  double ds = 0.0;
+  if (E.n > 0) {
+    ds = s - E.s_prev;
+    if (ds < 0.0) atomicCAS(P.status, 0, 749);
+    if (ir == 1 && E.ir_old == 1 && icr == 1 && E.icr_old == 1) { ds = 0.0; flag |= kFlagInit; }
+    if (!(ir > 1)) {
+      if (P.in_itype == 1) {
+        if (E.ir_old == 1 && E.icr_old == 1) flag |= kFlagZero | kFlagInit;
+      } else if (P.in_itype == 2) {
+        if (ir == 1 && !E.star_done && iray == 0 && P.rbeam0_center > 0.0) {
+          if (P.rbeam0_center < P.rstar) atomicCAS(P.status, 0, 124);
+          flag |= kFlagStar | kFlagInit;
+          E.star_done = 1;
+        }
+      } else {
+        atomicCAS(P.status, 0, 13);  // inner BC 0 disabled / unknown (telescope.F:4129-4134, 4210)
+      }
+    }
+  }
+  P.nodes.ds[idx] = ds;
+  P.nodes.dvmu[idx] = dvmu;
+  P.nodes.lw[idx] = lw;
+  P.nodes.wr[idx] = dr;
+  P.nodes.wt[idx] = dt;
+  P.nodes.cell[idx] = cells;
+  P.nodes.flag[idx] = flag;
+  E.ir_old = ir;
+  E.icr_old = icr;
+  E.s_prev = s;
+  E.n++;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
+  const int iray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iray >= P.nray) return;
+  const GridDev &g = P.g;
+  const int nr = g.nr, nt = g.nt;
+  Ray R;
+  R.g = g;
+  R.x0 = P.x0[iray];
+  R.z0 = P.z0[iray];
+  R.rstar = P.rstar;
+  const double theta0 = P.theta0;
+  R.pitheta0 = 0.5 * kPi - theta0;
+  R.costh0 = cos(theta0);
+  R.sinth0 = sin(theta0);
+  R.costh02 = R.costh0 * R.costh0;
+  R.sinth02 = R.sinth0 * R.sinth0;
+  const double x0 = R.x0, z0 = R.z0;
+  const double eps = kTelescEps, epsplus = 1.e1 * kTelescEps;
+
+  // ---- theta crossings: which cones are hit (telescope.F:2958-3014) ----
+  {
+    int cnt = 0, first = 0, dbl = 0;
+    const int iyeq = nt / 2;
+    for (int iy = 1; iy <= iyeq; iy++) {
+      double a1, a2;
+      if (th_roots(R, iy, a1, a2)) {
+        if (cnt == 0) first = iy;
+        cnt++;
+        double pitheta = 0.5 * kPi - TCf(g, iy);
+        if (fabs(pitheta) > fabs(R.pitheta0)) dbl++;
+      }
+    }
+    // hit cones form a contiguous tail iy_first..nth (disc>0 <=> tan^2 theta above a threshold)
+    if (cnt > 0 && first + cnt - 1 != iyeq) atomicCAS(P.status, 0, 9001);
+    R.isnr = cnt;
+    R.isdbl = dbl;
+    R.iy_first = first;
+    R.iup = (R.pitheta0 > 0.0) ? 1 : 0;
+    R.branchA = (z0 * R.pitheta0 > 0.0) ? 1 : 0;
+    R.ith_amount = 2 * cnt;
+  }
+  // ---- R crossings (telescope.F:3241-3276) ----
+  const double bimpact = sqrt(x0 * x0 + z0 * z0 * (1.0 - R.costh02));
+  {
+    int ix;
+    for (ix = 1; ix <= nr; ix++)
+      if (RCf(g, ix) > bimpact) break;
+    if (ix > nr) {
+      atomicCAS(P.status, 0, 13);
+      if (COUNT) P.node_cnt[iray] = 0;
+      return;
+    }
+    R.ir_min = ix;
+    if (bimpact <= P.rstar) R.ir_min = 0;
+    R.ir_amount = 2 * (nr + 1 - R.ir_min);
+  }
+  const double rmaxt = RCf(g, nr) * (1.0 - epsplus);
+  const double rmaxr = RCf(g, nr) * (1.0 + epsplus);
+  const double rmint = RCf(g, 1) * (1.0 + epsplus);
+  const double rminr = RCf(g, 1) * (1.0 - epsplus);
+  const double send = 1.e30, sbeg = -1.e30;
+
+  // ---- extremum sampling points (telescope.F:3417-3600) ----
+  Extra ex[kMaxExtra];
+  int nex = 0;
+  if (bimpact > RCf(g, 1)) {
+    double s2 = 0.0 - z0 * R.costh0;
+    ex[nex].s = s2;
+    ex[nex].radius = bimpact;
+    ex[nex].theta = theta_of_s(R, s2);
+    ex[nex].ir = R.ir_min - 1;
+    ex[nex].it = hunt_bisect(g.tc + 2, nt, ex[nex].theta);
+    nex++;
+    const double s3 = s2;
+    // hunt0(r_s, ir_amount, s2): largest k with r_s(k) < s2
+    int isrt;
+    {
+      int jlo = 0, jhi = R.ir_amount + 1;
+      while (jhi - jlo != 1) {
+        int jm = (jhi + jlo) >> 1;
+        if (s2 > r_s_at(R, jm)) jlo = jm;
+        else jhi = jm;
+      }
+      isrt = jlo;
+    }
+    for (int irng = 1; irng <= 4; irng++) {
+      double s1;
+      if (irng == 1) { s1 = s3; s2 = r_s_at(R, isrt + 1); }
+      else if (irng == 2) { s1 = r_s_at(R, isrt); s2 = s3; }
+      else if (irng == 3) { s1 = r_s_at(R, isrt + 1); s2 = r_s_at(R, isrt + 2); }
+      else { s1 = r_s_at(R, isrt - 1); s2 = r_s_at(R, isrt); }
+      double ds = (s2 - s1) / (1.0 + 1.0 * kRayAdpt);
+      for (int iad = 1; iad <= kRayAdpt; iad++) {
+        double s0 = iad * ds + s1;
+        ex[nex].s = s0;
+        ex[nex].radius = radius_of_s(R, s0);
+        ex[nex].theta = theta_of_s(R, s0);
+        ex[nex].ir = hunt_bisect(g.rc + 2, nr, ex[nex].radius);
+        ex[nex].it = hunt_bisect(g.tc + 2, nt, ex[nex].theta);
+        nex++;
+      }
+    }
+  }
+  {
+    double s2 = x0 * x0 * R.costh0 / (z0 * R.sinth02);  // NaN for the centre ray: falls through
+    double rr = radius_of_s(R, s2);
+    if (rr > RCf(g, 1) && rr < RCf(g, nr)) {
+      ex[nex].s = s2;
+      ex[nex].radius = rr;
+      ex[nex].theta = theta_of_s(R, s2);
+      int ix = hunt_bisect(g.rc + 2, nr, rr);
+      if (ix == 0 || ix == nr) atomicCAS(P.status, 0, 192);
+      ex[nex].ir = ix;
+      ex[nex].it = hunt_bisect(g.tc + 2, nt, ex[nex].theta);
+      nex++;
+      const double s3 = s2;
+      int isrt;
+      {
+        int jlo = 0, jhi = R.ith_amount + 1;
+        while (jhi - jlo != 1) {
+          int jm = (jhi + jlo) >> 1;
+          if (s3 > th_s_at(R, jm)) jlo = jm;
+          else jhi = jm;
+        }
+        isrt = jlo;
+      }
+      if (!((isrt - kRayRnpt + 1 < 1) || (isrt + kRayRnpt > R.ith_amount))) {
+        for (int irng = 1; irng <= 4; irng++) {
+          double s1;
+          if (irng == 1) { s1 = s3; s2 = th_s_at(R, isrt + 1); }
+          else if (irng == 2) { s1 = th_s_at(R, isrt); s2 = s3; }
+          else if (irng == 3) { s1 = th_s_at(R, isrt + 1); s2 = th_s_at(R, isrt + 2); }
+          else { s1 = th_s_at(R, isrt - 1); s2 = th_s_at(R, isrt); }
+          if (s2 == s1) atomicCAS(P.status, 0, 987);
+          if (s2 < s1) atomicCAS(P.status, 0, 988);
+          double ds = (s2 - s1) / (1.0 + 1.0 * kRayAdpt);
+          for (int iad = 1; iad <= kRayAdpt; iad++) {
+            double s0 = iad * ds + s1;
+            double rad = radius_of_s(R, s0);
+            int ixx = hunt_bisect(g.rc + 2, nr, rad);
+            if (ixx == 0 || ixx == nr) continue;
+            ex[nex].s = s0;
+            ex[nex].radius = rad;
+            ex[nex].theta = theta_of_s(R, s0);
+            ex[nex].ir = ixx;
+            ex[nex].it = hunt_bisect(g.tc + 2, nt, ex[nex].theta);
+            nex++;
+          }
+        }
+      }
+    }
+  }
+  // sort the extra points by s (nrecip.F:833 ray_sort); insertion sort, n <= 34
+  for (int i = 1; i < nex; i++) {
+    Extra e = ex[i];
+    int j = i - 1;
+    while (j >= 0 && ex[j].s > e.s) {
+      ex[j + 1] = ex[j];
+      j--;
+    }
+    ex[j + 1] = e;
+  }
+
+  // ---- 3-way merge by s (telescope.F:3607-3677) ----
+  const double znew = z0 * R.sinth02;
+  const double bnew = sqrt(x0 * x0 + z0 * z0 * R.sinth02);
+  const long long base = COUNT ? 0 : P.node_off[iray];
+  Emit E;
+  E.n = 0;
+  E.ir_old = -99;
+  E.icr_old = -99;
+  E.s_prev = 0.0;
+  E.star_done = 0;
+  double sprev = -1.e30;
+  int ist = 1, isr = 1, isex = 0;
+  double th_s = 1.e30, r_s = 1.e30, r_rad = 0.0;
+  int th_it = 0, r_ix = 0;
+  if (ist <= R.ith_amount) th_elem(R, ist, th_s, th_it);
+  if (isr <= R.ir_amount) r_elem(R, isr, r_s, r_ix, r_rad);
+  const int total = R.ir_amount + R.ith_amount;
+  for (int iss = 1; iss <= total; iss++) {
+    for (;;) {
+      double exs = (isex < nex) ? ex[isex].s : 1.e30;
+      if (!(exs < fmin(th_s, r_s))) break;
+      const Extra &e = ex[isex];
+      if (e.radius <= rmaxt && e.radius >= rmint && (e.s - sprev) > eps * e.radius && e.s >= sbeg &&
+          e.s <= send) {
+        emit_node<COUNT>(P, R, E, base, iray, 3, e.radius, e.theta, e.ir, e.it, e.s, znew, bnew);
+        sprev = e.s;
+      }
+      isex++;
+    }
+    if (th_s < r_s) {
+      double th_rad = radius_of_s(R, th_s);
+      if (th_rad <= rmaxt && th_rad >= rmint && (th_s - sprev) > eps * th_rad && th_s >= sbeg &&
+          th_s <= send) {
+        int th_ir;
+        if (th_rad < RCf(g, 1)) th_ir = 0;
+        else if (th_rad > RCf(g, nr)) th_ir = nr;
+        else th_ir = hunt_bisect(g.rc + 2, nr, th_rad);
+        emit_node<COUNT>(P, R, E, base, iray, 2, th_rad, TCf(g, th_it), th_ir, th_it, th_s, znew, bnew);
+        sprev = th_s;
+      }
+      ist++;
+      if (ist <= R.ith_amount) th_elem(R, ist, th_s, th_it);
+      else th_s = 1.e30;
+    } else {
+      if (r_rad <= rmaxr && r_rad >= rminr && (r_s - sprev) > eps * r_rad && r_s >= sbeg && r_s <= send) {
+        double th = theta_of_s(R, r_s);
+        int it = hunt_bisect(g.tc + 2, nt, th);
+        emit_node<COUNT>(P, R, E, base, iray, 1, r_rad, th, r_ix, it, r_s, znew, bnew);
+        sprev = r_s;
+      }
+      isr++;
+      if (isr <= R.ir_amount) r_elem(R, isr, r_s, r_ix, r_rad);
+      else r_s = 1.e30;
+    }
+  }
+  if (COUNT) P.node_cnt[iray] = E.n;
+}
+
+}  // namespace
+
+void launch_geom(const GeomParams &P, bool count, cudaStream_t st) {
+  const int threads = 128;
+  const int blocks = (P.nray + threads - 1) / threads;
+  if (count) geom_kernel<true><<<blocks, threads, 0, st>>>(P);
+  else geom_kernel<false><<<blocks, threads, 0, st>>>(P);
+}
+
+}  // namespace rl

@@ -1,0 +1,132 @@
+// rl_types.h -- shared host/device types of libradlite_b200 (internal, not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rl {
+
+// reference compile-time constants (configure.h:46, main.h:452-453, common_telescope.h:4-6)
+constexpr double kTelescEps = 1.0e-10;
+constexpr double kPi = 3.1415926535897932385;
+constexpr double kTempCmb = 2.728;
+constexpr int kRayAdpt = 4;
+constexpr int kRayRnpt = 4;
+constexpr int kMaxExtra = 40;  // 2 + 4*RAYADPT*2 = 34 used
+constexpr int kLgNrMax = 31;   // line.F:4657-4661
+
+// node flags (low 2 bits = tr_icross: 1 = R crossing, 2 = theta crossing, 3 = extra point)
+constexpr uint32_t kFlagIcrMask = 3u;
+constexpr uint32_t kFlagInit = 4u;   // carried profile state is reset before this segment
+constexpr uint32_t kFlagStar = 8u;   // centre beam: mix in the star before this segment
+constexpr uint32_t kFlagZero = 16u;  // inner BC type 1: intensity := 0 before this segment
+
+// ghosted grids: rc[i+1] = rsi_x_c(i,1), i=-1..nr+2 ; tc[i+1] = rsi_x_c(i,2), i=-1..nt+2 ;
+// ridx[i+4] = ridx_it(i), i=-4..nt+4
+struct GridDev {
+  int nr, nt, nth;
+  const double *rc;
+  const double *tc;
+  const int *ridx;
+};
+
+// Line-independent per-cell fields, one 32-byte record per cell: {linewidth, v_r, v_theta, v_phi}
+// Per-line per-cell fields, one 32-byte record: {src_dust, alp_dust, N_up, N_down}
+// Cell index = (ir-1)*nth + (it-1): the Fortran (it,ir) order.
+
+// Node lists of all rays, structure of arrays, ray r owns [node_off[r], node_off[r+1]).
+struct NodesDev {
+  double *ds;    // segment length to the previous node (vacuum rule applied); 0 for a ray's first node
+  double *dvmu;  // Omega.v/c at the node (line independent)
+  double *lw;    // interpolated line width [km/s]
+  double *wr;    // dr
+  double *wt;    // dt
+  int4 *cell;    // cells (t0,r0), (t1,r0), (t0,r1), (t1,r1)
+  uint32_t *flag;
+};
+
+struct GeomParams {
+  GridDev g;
+  int nray;
+  const double *x0;  // [nray]
+  const double *z0;
+  double theta0;
+  double rstar;
+  int in_itype;
+  double rbeam0_center;  // imcir_ri(1): star mixing of the centre ray
+  const double4 *cellS;  // {lw, v1, v2, v3}
+  const long long *node_off;  // [nray+1] (fill pass)
+  int *node_cnt;              // [nray]   (count pass)
+  NodesDev nodes;
+  int *status;  // first error code (reference stop code), 0 = ok
+};
+
+// per-line constants (host-prepared, line.F:427-545, 1708-1788, 3797-3903)
+struct LineDev {
+  double nu0;       // linefreq = line_nu0
+  double aud;       // Aud
+  double bud, bdu;  // Einstein B's
+  double dnu0;      // line_dnu(1)
+  double ddnu;      // channel spacing dnu
+  double i_outer;   // outer-BC start intensity for out_itype 0/2 (type 3: per channel array)
+};
+
+struct RenderParams {
+  GridDev g;
+  int nray, nphi, nrr;
+  int nl;    // lines in this batch
+  int nfr;
+  int subgrid, nonredundant;
+  double levthres;
+  double aksmax_c;  // aksmax/2.99792458d5
+  double starfract;  // (rstar/rbeam0)^2 for the centre ray
+  int out_itype;
+  const long long *node_off;
+  NodesDev nodes;
+  const double4 *cellL;  // [nl][ncell]
+  long long ncell;
+  const LineDev *lines;      // [nl]
+  const double *line_dnu;    // [nl][nfr]
+  const double *velo;        // [nl][nfr]
+  const double *star_line;   // [nl][nfr]
+  const double *isrf_line;   // [nl][nfr]
+  // per task (line_local*nray + ray)
+  int4 *rng;                 // {lo, hi, c0, ch0_in_range}
+  unsigned int *nitems;      // [ntask]
+  const unsigned int *item_off;  // [ntask+1]
+  double *img;               // [nl][nrr+1][nphi][nfr]
+  unsigned char *integ;      // [nl][nrow][nfr] 1 = channel was integrated with cmask=1
+  double *tau_center;        // [nl]
+  int *maser;                // [nl]
+  unsigned long long *counters;  // {R, E, S}
+  int *status;
+};
+
+// per-line preparation (prep_cells_kernel)
+struct PrepParams {
+  long long ncell;
+  int nl;
+  int nlevels;
+  const double *popul;   // [ncell][nlevels]
+  const double *abund;   // [ncell]
+  const double *rho;     // [ncell]
+  double molpg;
+  const int *lev_up;     // [nl] (1-based)
+  const int *lev_down;
+  // dust
+  int use_dust;          // 1: compute from dust tables, 0: ld_src/ld_alp given
+  int nspec, maxsize, ncf;
+  const int *nsize;
+  const double *kabs;    // [nspec][maxsize][ncf]
+  const double *kscat;
+  const double *drho;    // [ncell][nspec]
+  const double *dtemp;   // [ncell][nspec][maxsize]
+  const double *scat;    // [ncell][ncf] or null
+  const int *inudust;    // [nl] hunt result on cont_freq_nu (1-based), 0 or ncf = outside
+  const double *wgt;     // [nl]
+  const double *freq;    // [nl]
+  const double *ld_src;  // [nl][ncell]
+  const double *ld_alp;
+  double4 *cellL;        // [nl][ncell]
+};
+
+}  // namespace rl
