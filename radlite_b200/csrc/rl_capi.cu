@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -67,6 +68,7 @@ struct rl_ctx {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   long long launches = 0;
+  int cpt = kChanPerThread;  // tunable through RADLITE_B200_CPT (1..4)
   // grid
   int nr = 0, nt = 0, nth = 0;
   std::vector<double> rc, tc;
@@ -114,9 +116,7 @@ struct rl_ctx {
   DevBuf<int> d_node_cnt;
   DevBuf<long long> d_node_off;
   std::vector<long long> h_node_off;
-  DevBuf<double> d_nds, d_ndvmu, d_nlw, d_nwr, d_nwt;
-  DevBuf<int4> d_ncell;
-  DevBuf<uint32_t> d_nflag;
+  DevBuf<NodeRec> d_nrec;
   DevBuf<int> d_status;
   // render buffers
   DevBuf<double4> d_cellL;
@@ -188,6 +188,7 @@ int rl_create(rl_ctx **out, int device) {
     return -6;
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
+  if (const char *e = getenv("RADLITE_B200_CPT")) c->cpt = std::max(1, std::min(4, atoi(e)));
   c->d_status.ensure(1);
   c->d_counters.ensure(3);
   cudaMemsetAsync(c->d_counters.p, 0, 3 * sizeof(unsigned long long), c->st);
@@ -536,13 +537,7 @@ static GridDev grid_dev(rl_ctx *c) {
 
 static NodesDev nodes_dev(rl_ctx *c) {
   NodesDev n;
-  n.ds = c->d_nds.p;
-  n.dvmu = c->d_ndvmu.p;
-  n.lw = c->d_nlw.p;
-  n.wr = c->d_nwr.p;
-  n.wt = c->d_nwt.p;
-  n.cell = c->d_ncell.p;
-  n.flag = c->d_nflag.p;
+  n.rec = c->d_nrec.p;
   return n;
 }
 
@@ -585,13 +580,8 @@ static int ensure_geometry(rl_ctx *c) {
   c->total_nodes = c->h_node_off[c->nray];
   CU(c->d_node_off.upload(c->h_node_off, c->st));
   const size_t n = (size_t)c->total_nodes;
-  CU(c->d_nds.ensure(n));
-  CU(c->d_ndvmu.ensure(n));
-  CU(c->d_nlw.ensure(n));
-  CU(c->d_nwr.ensure(n));
-  CU(c->d_nwt.ensure(n));
-  CU(c->d_ncell.ensure(n));
-  CU(c->d_nflag.ensure(n));
+  if ((size_t)c->nr * c->nth > (size_t)kCellMask) return fail(c, 13, "grid has too many cells for the node record");
+  CU(c->d_nrec.ensure(n));
   P.node_off = c->d_node_off.p;
   P.nodes = nodes_dev(c);
   launch_geom(P, false, c->st);
@@ -792,6 +782,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.nfr = nfr;
     P.subgrid = c->subgrid;
     P.nonredundant = c->nonredundant;
+    P.cpt = c->cpt;
     P.levthres = c->levthres;
     P.aksmax_c = aksmax / 2.99792458e5;
     {
@@ -965,16 +956,24 @@ int rl_get_ray_nodes(rl_ctx *c, int iray, double *ds, double *dvmu, double *lw, 
   if (rcode) return -std::abs(rcode);
   if (iray < 1 || iray > c->nray) return -13;
   const long long n0 = c->h_node_off[iray - 1], n = c->h_node_off[iray] - n0;
-  auto cp = [&](void *dst, const void *src, size_t bytes) {
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->st);
-  };
-  if (ds) cp(ds, c->d_nds.p + n0, n * 8);
-  if (dvmu) cp(dvmu, c->d_ndvmu.p + n0, n * 8);
-  if (lw) cp(lw, c->d_nlw.p + n0, n * 8);
-  if (wr) cp(wr, c->d_nwr.p + n0, n * 8);
-  if (wt) cp(wt, c->d_nwt.p + n0, n * 8);
-  if (cells4) cp(cells4, c->d_ncell.p + n0, n * 16);
-  if (flags) cp(flags, c->d_nflag.p + n0, n * 4);
+  std::vector<NodeRec> h((size_t)n);
+  cudaMemcpyAsync(h.data(), c->d_nrec.p + n0, (size_t)n * sizeof(NodeRec), cudaMemcpyDeviceToHost, c->st);
+  cudaStreamSynchronize(c->st);
+  for (long long i = 0; i < n; i++) {
+    const NodeRec &r = h[(size_t)i];
+    if (ds) ds[i] = r.ds;
+    if (dvmu) dvmu[i] = r.dvmu;
+    if (lw) lw[i] = r.lw;
+    if (wr) wr[i] = r.wr;
+    if (wt) wt[i] = r.wt;
+    if (cells4) {
+      cells4[4 * i] = r.cells.x & kCellMask;
+      cells4[4 * i + 1] = r.cells.y;
+      cells4[4 * i + 2] = r.cells.z;
+      cells4[4 * i + 3] = r.cells.w;
+    }
+    if (flags) flags[i] = (int)((unsigned)r.cells.x >> kCellFlagShift);
+  }
   cudaStreamSynchronize(c->st);
   return (int)n;
 }

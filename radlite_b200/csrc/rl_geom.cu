@@ -135,7 +135,7 @@ struct Emit {
   // running state of charintline's node loop
   int n;
   int ir_old, icr_old;
-  double s_prev;
+  double s_prev, dvmu_prev, lw_prev;
   int star_done;
 };
 
@@ -224,13 +224,24 @@ __device__ void emit_node(const GeomParams &P, const Ray &R, Emit &E, long long 
       }
     }
   }
-  P.nodes.ds[idx] = ds;
-  P.nodes.dvmu[idx] = dvmu;
-  P.nodes.lw[idx] = lw;
-  P.nodes.wr[idx] = dr;
-  P.nodes.wt[idx] = dt;
-  P.nodes.cell[idx] = cells;
-  P.nodes.flag[idx] = flag;
+  // sub-grid trigger of the segment ending here (line.F:4706-4709)
+  double q = 0.0;
+  if (E.n > 0) {
+    const double lwseg = 0.5 * (E.lw_prev + lw);
+    q = fabs((dvmu - E.dvmu_prev) / (lwseg / 2.99792458e5));
+  }
+  NodeRec rec;
+  rec.ds = ds;
+  rec.dvmu = dvmu;
+  rec.lw = lw;
+  rec.q = q;
+  rec.wr = dr;
+  rec.wt = dt;
+  cells.x |= (int)(flag << kCellFlagShift);
+  rec.cells = cells;
+  P.nodes.rec[idx] = rec;
+  E.dvmu_prev = dvmu;
+  E.lw_prev = lw;
   E.ir_old = ir;
   E.icr_old = icr;
   E.s_prev = s;
@@ -410,6 +421,8 @@ __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
   E.ir_old = -99;
   E.icr_old = -99;
   E.s_prev = 0.0;
+  E.dvmu_prev = 0.0;
+  E.lw_prev = 0.0;
   E.star_done = 0;
   double sprev = -1.e30;
   int ist = 1, isr = 1, isex = 0;

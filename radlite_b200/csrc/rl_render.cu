@@ -7,7 +7,11 @@
 //   integrate_kernel    telescope.F:3889-4312 (charintline), line.F:4636-4848
 //                       (clever_integrate_element_linedust), line.F:4515-4624
 //                       (integrate_element_linedust), line.F:2280 (voigt_profile),
-//                       transfer.F:1498 (qdr_src_2): one thread per (line, ray, channel) item
+//                       transfer.F:1498 (qdr_src_2).  One thread carries kChanPerThread velocity
+//                       channels of one (line, ray): the node record, the bilinear gather of the
+//                       per-line cell fields and the per-segment profile constants are computed
+//                       once and shared by the channels, which also gives the FP64 pipe
+//                       kChanPerThread independent dependency chains per thread.
 //   fill_kernel         telescope.F:582-612 continuum copy for the skipped channels
 //   ringsum/flux        telescope.F:1388-1433 (calc_freq_flux_observer), fixed summation order
 #include "rl_types.h"
@@ -22,6 +26,29 @@ __device__ __forceinline__ double4 ldg4(const double4 *p) {
   const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
   const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
   return make_double4(a.x, a.y, b.x, b.y);
+}
+
+struct Node {
+  double ds, dvmu, lw, q, wr, wt;
+  int4 cells;
+  uint32_t flags;
+};
+
+__device__ __forceinline__ Node load_node(const NodeRec *__restrict__ rec, long long i) {
+  const double2 *p = reinterpret_cast<const double2 *>(rec + i);
+  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  const int4 d = __ldg(reinterpret_cast<const int4 *>(p + 3));
+  Node n;
+  n.ds = a.x;
+  n.dvmu = a.y;
+  n.lw = b.x;
+  n.q = b.y;
+  n.wr = c.x;
+  n.wt = c.y;
+  n.cells = d;
+  n.flags = (uint32_t)d.x >> kCellFlagShift;
+  n.cells.x = d.x & kCellMask;
+  return n;
 }
 
 // interpolate the per-line cell record {src_dust, alp_dust, N_up, N_down} at a node
@@ -54,7 +81,6 @@ __device__ __forceinline__ double4 gather_line(const double4 *__restrict__ cellL
 // ------------------------------------------------------------------------------------------
 // per-line preparation
 // ------------------------------------------------------------------------------------------
-
 __device__ __forceinline__ double bplanck_dev(double temp, double nu) {
   if (temp == 0.0) return 0.0;
   return 1.47455e-47 * nu * nu * nu / (exp(4.7989e-11 * nu / temp) - 1.0) + 1.e-290;
@@ -116,7 +142,8 @@ __global__ void __launch_bounds__(256) span_kernel(RenderParams P) {
   if (ray == 0 || !P.nonredundant) {
     if (lane == 0) {
       P.rng[task] = make_int4(1, P.nfr - 1, -1, ray == 0 ? 2 : 1);
-      P.nitems[task] = P.nfr;
+      // the centre ray keeps one channel per thread (it also produces char_tau_center)
+      P.nitems[task] = ray == 0 ? P.nfr : (P.nfr + P.cpt - 1) / P.cpt;
     }
     return;
   }
@@ -125,12 +152,11 @@ __global__ void __launch_bounds__(256) span_kernel(RenderParams P) {
   double vmin = 2.0, vmax = -2.0;
   // telescope.F:4265-4270: start node of every segment, i.e. all nodes but the last
   for (long long i = n0 + lane; i < n1 - 1; i += 32) {
-    const uint32_t fl = P.nodes.flag[i];
-    const double4 v = gather_line(cellL, P.nodes.cell[i], P.nodes.wr[i], P.nodes.wt[i], fl & kFlagIcrMask);
+    const Node nd = load_node(P.nodes.rec, i);
+    const double4 v = gather_line(cellL, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
     if (v.z + v.w > P.levthres) {
-      const double dv = P.nodes.dvmu[i];
-      vmin = fmin(vmin, dv);
-      vmax = fmax(vmax, dv);
+      vmin = fmin(vmin, nd.dvmu);
+      vmax = fmax(vmax, nd.dvmu);
     }
   }
   for (int o = 16; o; o >>= 1) {
@@ -171,15 +197,31 @@ __global__ void __launch_bounds__(256) span_kernel(RenderParams P) {
     }
     if (hi < lo) { lo = 1; hi = 0; }
     P.rng[task] = make_int4(lo, hi, c0i, ch0_out ? 0 : 1);
-    P.nitems[task] = (unsigned)n;
+    P.nitems[task] = (unsigned)((n + P.cpt - 1) / P.cpt);
   }
 }
 
+// number of channels the reference integrates for a task and the j-th of them
+__device__ __forceinline__ int task_nchan(const RenderParams &P, const int4 rg) {
+  if (rg.w == 2 || !P.nonredundant) return P.nfr;
+  return 1 + ((rg.y >= rg.x) ? (rg.y - rg.x + 1) : 0) + (rg.z >= 0 ? 1 : 0);
+}
+__device__ __forceinline__ int task_chan(const RenderParams &P, const int4 rg, int j, bool &masked) {
+  if (rg.w == 2) { masked = false; return j; }  // centre ray: the reference never sets its mask
+  if (!P.nonredundant) { masked = (j == 0); return j; }  // telescope.F:548 only
+  const int nin = (rg.y >= rg.x) ? (rg.y - rg.x + 1) : 0;
+  if (j == 0) { masked = true; return 0; }
+  if (j <= nin) { masked = true; return rg.x + j - 1; }
+  masked = false;
+  return rg.z;
+}
+
 // ------------------------------------------------------------------------------------------
-// the formal solution of one ray at one channel
+// the formal solution, reference-ordered scalar version: used for the centre ray (which also
+// yields char_tau_center), for sub-gridded segments and for the rare zero-continuum fallback
 // ------------------------------------------------------------------------------------------
 struct Carry {
-  double phiprof0, srcl0, alpl0;
+  double srcl0, alpl0;
   int init;
 };
 
@@ -213,21 +255,20 @@ __device__ __forceinline__ double qdr_src_2(double inten, double js1, double alp
 }
 
 // line.F:4515-4624 (+ voigt_profile line.F:2280-2314)
-__device__ __forceinline__ void integrate_element(const LineDev &L, double dnu_ch, double &inten,
-                                                  double ds, double srcd0, double srcd1,
-                                                  double alpd0, double alpd1, double lw0, double lw1,
-                                                  double dvmu0, double dvmu1, double nup0,
-                                                  double nup1, double ndown0, double ndown1,
-                                                  Carry &k, double &tau) {
+__device__ __noinline__ void integrate_element(const LineDev &L, double dnu_ch, double &inten,
+                                               double ds, double srcd0, double srcd1, double alpd0,
+                                               double alpd1, double lw0, double lw1, double dvmu0,
+                                               double dvmu1, double nup0, double nup1,
+                                               double ndown0, double ndown1, Carry &k, double &tau) {
   const double lwav = 0.5 * (lw0 + lw1);
   const double aa = 3.33567e-6 * L.nu0 * lwav;
   const double norm = 0.56419583546 / aa;
   if (k.init) {
     const double dnu0 = dnu_ch - L.nu0 * dvmu0;
     const double u0 = dnu0 / aa;
-    k.phiprof0 = norm * exp(-(u0 * u0));
-    k.srcl0 = 5.27296241956e-28 * L.nu0 * nup0 * L.aud * k.phiprof0;
-    k.alpl0 = 5.27296241956e-28 * L.nu0 * k.phiprof0 * (ndown0 * L.bdu - nup0 * L.bud);
+    const double phiprof0 = norm * exp(-(u0 * u0));
+    k.srcl0 = 5.27296241956e-28 * L.nu0 * nup0 * L.aud * phiprof0;
+    k.alpl0 = 5.27296241956e-28 * L.nu0 * phiprof0 * (ndown0 * L.bdu - nup0 * L.bud);
   }
   const double dnu1 = dnu_ch - L.nu0 * dvmu1;
   const double u1 = dnu1 / aa;
@@ -238,16 +279,44 @@ __device__ __forceinline__ void integrate_element(const LineDev &L, double dnu_c
   const double alp0 = alpd0 + k.alpl0, alp1 = alpd1 + alpl1;
   inten = qdr_src_2(inten, src0, alp0, src1, alp1, ds);
   tau = tau + 0.5 * (alp0 + alp1) * ds;
-  k.phiprof0 = phiprof1;
   k.srcl0 = srcl1;
   k.alpl0 = alpl1;
   k.init = 0;
 }
 
-// telescope.F:3889-4312 for ray `ray`, channel `ch` (0-based) of line slot `l`.
-// Returns the intensity; counts element integrations in nelem.
-__device__ double integrate_ray_channel(const RenderParams &P, int l, int ray, int ch, double &tau,
-                                        unsigned &nelem, int &maser) {
+// the sub-gridded segment of line.F:4745-4833: returns the number of element integrations
+__device__ __noinline__ int subgrid_segment(const LineDev &L, double dnu_ch, double &inten, double ds,
+                                            double sleft, double sright, const double4 &v0,
+                                            const double4 &v1, double dvmu0, double dvmu1, double lw,
+                                            Carry &k, double &tau) {
+  const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
+  double sp = 0.0, nup_p = v0.z, ndn_p = v0.w, dv_p = dvmu0, sd_p = v0.x, ad_p = v0.y;
+  int n = 0;
+  for (int j = 1; j <= kLgNrMax + 1; j++) {
+    double s, nup_c, ndn_c, dv_c, sd_c, ad_c;
+    if (j <= kLgNrMax) {
+      s = sleft + (j - 1) * lg_ds;
+      if (!(s > 0.0 && s < ds)) continue;
+      const double eps = s / ds, epsp = 1.0 - eps;
+      nup_c = epsp * v0.z + eps * v1.z;
+      ndn_c = epsp * v0.w + eps * v1.w;
+      dv_c = epsp * dvmu0 + eps * dvmu1;
+      sd_c = epsp * v0.x + eps * v1.x;
+      ad_c = epsp * v0.y + eps * v1.y;
+    } else {
+      s = ds; nup_c = v1.z; ndn_c = v1.w; dv_c = dvmu1; sd_c = v1.x; ad_c = v1.y;
+    }
+    integrate_element(L, dnu_ch, inten, s - sp, sd_p, sd_c, ad_p, ad_c, lw, lw, dv_p, dv_c, nup_p,
+                      nup_c, ndn_p, ndn_c, k, tau);
+    n++;
+    sp = s; nup_p = nup_c; ndn_p = ndn_c; dv_p = dv_c; sd_p = sd_c; ad_p = ad_c;
+  }
+  return n;
+}
+
+// telescope.F:3889-4312 for ray `ray`, channel `ch` (0-based) of line slot `l`, reference order
+__device__ __noinline__ double integrate_ray_channel(const RenderParams &P, int l, int ray, int ch,
+                                                     double &tau, unsigned &nelem, int &maser) {
   const LineDev L = P.lines[l];
   const double4 *__restrict__ cellL = P.cellL + (size_t)l * P.ncell;
   const long long n0 = P.node_off[ray], n1 = P.node_off[ray + 1];
@@ -259,55 +328,30 @@ __device__ double integrate_ray_channel(const RenderParams &P, int l, int ray, i
   if (n1 <= n0) return inten;
   Carry k;
   k.init = 1;
-  k.phiprof0 = k.srcl0 = k.alpl0 = 0.0;
-  uint32_t fl = P.nodes.flag[n0];
-  double4 v0 = gather_line(cellL, P.nodes.cell[n0], P.nodes.wr[n0], P.nodes.wt[n0], fl & kFlagIcrMask);
-  double dvmu0 = P.nodes.dvmu[n0], lw0 = P.nodes.lw[n0];
+  k.srcl0 = k.alpl0 = 0.0;
+  Node nd = load_node(P.nodes.rec, n0);
+  double4 v0 = gather_line(cellL, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
+  double dvmu0 = nd.dvmu, lw0 = nd.lw;
   for (long long i = n0 + 1; i < n1; i++) {
-    fl = P.nodes.flag[i];
-    const double ds = P.nodes.ds[i];
-    const double dvmu1 = P.nodes.dvmu[i], lw1 = P.nodes.lw[i];
-    const double4 v1 = gather_line(cellL, P.nodes.cell[i], P.nodes.wr[i], P.nodes.wt[i], fl & kFlagIcrMask);
+    nd = load_node(P.nodes.rec, i);
+    const uint32_t fl = nd.flags;
+    const double ds = nd.ds, dvmu1 = nd.dvmu, lw1 = nd.lw;
+    const double4 v1 = gather_line(cellL, nd.cells, nd.wr, nd.wt, fl & kFlagIcrMask);
     if (fl & (kFlagInit | kFlagStar | kFlagZero)) {
       if (fl & kFlagZero) inten = 0.0;
       if (fl & kFlagStar)
         inten = (1.0 - P.starfract) * inten + P.starfract * P.star_line[(size_t)l * P.nfr + ch];
       k.init = 1;
     }
-    // line.F:4636-4848
     bool done = false;
-    if (P.subgrid) {
-      const double lw = 0.5 * (lw0 + lw1);
-      const double ds_over_deltal_s = fabs((dvmu1 - dvmu0) / (lw / 2.99792458e5));
-      if (2.0 * 3.0 * ds_over_deltal_s > 1.0) {
-        const double s_c = ds * (velo_ch - dvmu0) / (dvmu1 - dvmu0);
-        const double dls = ds / ds_over_deltal_s;
-        const double sright = s_c + 3.0 * dls;
-        const double sleft = s_c - 3.0 * dls;
-        if (sright > 0.0 && sleft < ds) {
-          const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
-          double sp = 0.0, nup_p = v0.z, ndn_p = v0.w, dv_p = dvmu0, sd_p = v0.x, ad_p = v0.y;
-          for (int j = 1; j <= kLgNrMax + 1; j++) {
-            double s, nup_c, ndn_c, dv_c, sd_c, ad_c;
-            if (j <= kLgNrMax) {
-              s = sleft + (j - 1) * lg_ds;
-              if (!(s > 0.0 && s < ds)) continue;
-              const double eps = s / ds, epsp = 1.0 - eps;
-              nup_c = epsp * v0.z + eps * v1.z;
-              ndn_c = epsp * v0.w + eps * v1.w;
-              dv_c = epsp * dvmu0 + eps * dvmu1;
-              sd_c = epsp * v0.x + eps * v1.x;
-              ad_c = epsp * v0.y + eps * v1.y;
-            } else {
-              s = ds; nup_c = v1.z; ndn_c = v1.w; dv_c = dvmu1; sd_c = v1.x; ad_c = v1.y;
-            }
-            integrate_element(L, dnu_ch, inten, s - sp, sd_p, sd_c, ad_p, ad_c, lw, lw, dv_p, dv_c,
-                              nup_p, nup_c, ndn_p, ndn_c, k, tau);
-            nelem++;
-            sp = s; nup_p = nup_c; ndn_p = ndn_c; dv_p = dv_c; sd_p = sd_c; ad_p = ad_c;
-          }
-          done = true;
-        }
+    if (P.subgrid && 2.0 * 3.0 * nd.q > 1.0) {  // line.F:4715
+      const double s_c = ds * (velo_ch - dvmu0) / (dvmu1 - dvmu0);
+      const double dls = ds / nd.q;
+      const double sright = s_c + 3.0 * dls, sleft = s_c - 3.0 * dls;
+      if (sright > 0.0 && sleft < ds) {
+        nelem += subgrid_segment(L, dnu_ch, inten, ds, sleft, sright, v0, v1, dvmu0, dvmu1,
+                                 0.5 * (lw0 + lw1), k, tau);
+        done = true;
       }
     }
     if (!done) {
@@ -327,61 +371,255 @@ __device__ __forceinline__ long long img_row(const RenderParams &P, int ray) {
   return ray == 0 ? 0 : (long long)P.nphi + (ray - 1);
 }
 
-// one thread per (line, ray, channel) item
-__global__ void __launch_bounds__(128) integrate_kernel(RenderParams P, unsigned total_items) {
+// reciprocal to ~1 ulp: hardware seed (2^-23) + two Newton steps.  Not correctly rounded; used
+// where the reference divides (source function j/alpha, e1/dtau) -- differences are O(1e-16).
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// exp(x) for x <= 0, branch free: x = n ln2 + r, |r| <= ln2/2, degree-12 Taylor polynomial
+// (truncation 1.7e-16), 2^n through the exponent field; below -708 the result is flushed to 0.
+__device__ __forceinline__ double exp_neg(double x) {
+  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);  // 1.5*2^52: round to nearest
+  const int n = __double2loint(t);
+  const double fn = t - 6755399441055744.0;
+  double r = fma(fn, -6.93147180369123816490e-01, x);
+  r = fma(fn, -1.90821492927058770002e-10, r);
+  double p = 2.08767569878680989792e-09;              // 1/12!
+  p = fma(p, r, 2.50521083854417187751e-08);          // 1/11!
+  p = fma(p, r, 2.75573192239858906526e-07);          // 1/10!
+  p = fma(p, r, 2.75573192239858906526e-06);          // 1/9!
+  p = fma(p, r, 2.48015873015873015873e-05);          // 1/8!
+  p = fma(p, r, 1.98412698412698412698e-04);          // 1/7!
+  p = fma(p, r, 1.38888888888888888889e-03);          // 1/6!
+  p = fma(p, r, 8.33333333333333333333e-03);          // 1/5!
+  p = fma(p, r, 4.16666666666666666667e-02);          // 1/4!
+  p = fma(p, r, 1.66666666666666666667e-01);          // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double scale = __hiloint2double((n + 1023) << 20, 0);
+  return (x < -708.0) ? 0.0 : p * scale;
+}
+
+// ------------------------------------------------------------------------------------------
+// integrate_kernel: one thread = (line, ray, up to kChanPerThread channels)
+// ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) integrate_kernel(RenderParams P, unsigned total_threads) {
   const unsigned item = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const long long ntask = (long long)P.nl * P.nray;
-  const bool active = item < total_items;
-  // the warp's first item -> task by binary search; later lanes walk forward
-  unsigned first = __shfl_sync(0xffffffffu, item, 0);
+  const bool active = item < total_threads;
+  // the warp's first work item -> task by binary search; later lanes walk forward
+  const unsigned first = __shfl_sync(0xffffffffu, item, 0);
   long long task = 0;
-  if (lane == 0 && first < total_items) {
+  if (lane == 0 && first < total_threads) {
     long long lo = 0, hi = ntask;  // largest t with item_off[t] <= first
     while (hi - lo > 1) {
-      long long mid = (lo + hi) >> 1;
+      const long long mid = (lo + hi) >> 1;
       if (P.item_off[mid] <= first) lo = mid;
       else hi = mid;
     }
     task = lo;
   }
   task = __shfl_sync(0xffffffffu, task, 0);
-  unsigned nelem = 0, nseg = 0;
+  unsigned long long nelem = 0, nseg = 0, nrc = 0;
   int maser = 0;
   if (active) {
     while (P.item_off[task + 1] <= item) task++;
     const int l = (int)(task / P.nray), ray = (int)(task % P.nray);
-    const unsigned j = item - P.item_off[task];
+    const int k = (int)(item - P.item_off[task]);
     const int4 rg = P.rng[task];
-    const int nin = (rg.y >= rg.x) ? (rg.y - rg.x + 1) : 0;
-    int ch;
-    bool masked;  // reference sets imcir_cmask=1 for this channel
-    if (rg.w == 2) { ch = (int)j; masked = false; }  // centre ray: the reference never sets its mask
-    else if (!P.nonredundant) { ch = (int)j; masked = (j == 0); }  // telescope.F:548 only
-    else if (j == 0) { ch = 0; masked = true; }
-    else if ((int)j <= nin) { ch = rg.x + (int)j - 1; masked = true; }
-    else { ch = rg.z; masked = false; }
-    double tau;
-    const double inten = integrate_ray_channel(P, l, ray, ch, tau, nelem, maser);
     const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
-    P.img[row * P.nfr + ch] = inten;
-    if (P.integ) P.integ[row * P.nfr + ch] = masked ? 1 : 2;
-    if (ray == 0 && ch == P.nfr - 1) P.tau_center[l] = tau;
+    double *__restrict__ Iout = P.img + row * P.nfr;
+    unsigned char *mout = P.integ ? P.integ + row * P.nfr : nullptr;
+    const long long n0 = P.node_off[ray], n1 = P.node_off[ray + 1];
+    if (ray == 0) {
+      // centre ray: one channel per thread, reference-ordered path (star mixing + char_tau_center)
+      double tau;
+      unsigned ne;
+      const double inten = integrate_ray_channel(P, l, 0, k, tau, ne, maser);
+      Iout[k] = inten;
+      if (mout) mout[k] = 2;
+      if (k == P.nfr - 1) P.tau_center[l] = tau;
+      nelem = ne;
+      nseg = (unsigned long long)(n1 - n0 - 1);
+      nrc = 1;
+    } else {
+      const LineDev L = P.lines[l];
+      const double4 *__restrict__ cellL = P.cellL + (size_t)l * P.ncell;
+      const int nch = task_nchan(P, rg);
+      int ch[C];
+      bool act[C], msk[C];
+      double dnu[C], inten[C], srcl0[C], alpl0[C], r0[C];
+      int nact = 0;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int j = k * C + c;
+        act[c] = j < nch;
+        msk[c] = false;
+        ch[c] = act[c] ? task_chan(P, rg, j, msk[c]) : 0;
+        dnu[c] = P.line_dnu[(size_t)l * P.nfr + ch[c]];
+        inten[c] = (P.out_itype == 3) ? P.isrf_line[(size_t)l * P.nfr + ch[c]] : L.i_outer;
+        srcl0[c] = alpl0[c] = r0[c] = 0.0;
+        nact += act[c] ? 1 : 0;
+      }
+      // per-line constants of line.F:4571-4588 and 2301-2302
+      const double k_aa = 3.33567e-6 * L.nu0;
+      const double c_src = 5.27296241956e-28 * L.nu0 * L.aud;
+      const double c_alp = 5.27296241956e-28 * L.nu0;
+      const double inv_nu0 = 1.0 / L.nu0;
+      unsigned initm = (1u << C) - 1u;  // channels whose carried line terms must be (re)computed
+      if (n1 > n0 + 1) {
+        Node nd = load_node(P.nodes.rec, n0);
+        double4 v0 = gather_line(cellL, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
+        double dvmu0 = nd.dvmu, lw0 = nd.lw;
+        // software pipeline: the record of node i+2 and the gathered cell values of node i+1 are
+        // in flight while segment (i-1, i) is integrated
+        const long long last = n1 - 1;
+        Node na = load_node(P.nodes.rec, n0 + 1);
+        double4 va = gather_line(cellL, na.cells, na.wr, na.wt, na.flags & kFlagIcrMask);
+        Node nb = load_node(P.nodes.rec, min(n0 + 2, last));
+        for (long long i = n0 + 1; i < n1; i++) {
+          nd = na;
+          const double4 v1 = va;
+          na = nb;
+          va = gather_line(cellL, na.cells, na.wr, na.wt, na.flags & kFlagIcrMask);
+          nb = load_node(P.nodes.rec, min(i + 2, last));
+          const uint32_t fl = nd.flags;
+          const double ds = nd.ds, dvmu1 = nd.dvmu, lw1 = nd.lw;
+          // per-segment quantities shared by the channels
+          const double lwav = 0.5 * (lw0 + lw1);
+          const double inv_aa = 1.0 / (k_aa * lwav);
+          const double norm = 0.56419583546 * inv_aa;
+          const double cN1 = c_src * v1.z;
+          const double kk1 = c_alp * (v1.w * L.bdu - v1.z * L.bud);
+          const double nudv1 = L.nu0 * dvmu1;
+          const double hds = 0.5 * ds;
+          if (fl & (kFlagInit | kFlagStar | kFlagZero)) {
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+              if (fl & kFlagZero) inten[c] = 0.0;
+              if (fl & kFlagStar)
+                inten[c] = (1.0 - P.starfract) * inten[c] + P.starfract * P.star_line[(size_t)l * P.nfr + ch[c]];
+            }
+            initm = (1u << C) - 1u;
+          }
+          unsigned donem = 0;  // channels handled by the sub-grid path in this segment
+          if (P.subgrid && (2.0 * 3.0 * nd.q > 1.0)) {  // line.F:4715 (rare)
+            const double inv_dd = 1.0 / (dvmu1 - dvmu0);
+            const double dls3 = 3.0 * (ds / nd.q);
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+              const double s_c = ds * (dnu[c] * inv_nu0 - dvmu0) * inv_dd;
+              const double sright = s_c + dls3, sleft = s_c - dls3;
+              if (act[c] && sright > 0.0 && sleft < ds) {
+                Carry kc;
+                kc.srcl0 = srcl0[c];
+                kc.alpl0 = alpl0[c];
+                kc.init = (initm >> c) & 1;
+                double tau = 0.0;
+                nelem += subgrid_segment(L, dnu[c], inten[c], ds, sleft, sright, v0, v1, dvmu0, dvmu1,
+                                         lwav, kc, tau);
+                srcl0[c] = kc.srcl0;
+                alpl0[c] = kc.alpl0;
+                r0[c] = (v1.x + kc.srcl0) * rcp_fast(v1.y + kc.alpl0);
+                initm &= ~(1u << c);
+                donem |= 1u << c;
+                if (kc.alpl0 * ds < (double)(-0.01f)) maser = 1;
+              }
+            }
+          }
+          if (initm) {  // first segment of the ray / after the inner hole (rare)
+            const double cN0 = c_src * v0.z;
+            const double kk0 = c_alp * (v0.w * L.bdu - v0.z * L.bud);
+            const double nudv0 = L.nu0 * dvmu0;
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              if ((initm >> c) & 1) {
+                const double u0 = (dnu[c] - nudv0) * inv_aa;
+                const double phi0 = norm * exp_neg(-(u0 * u0));
+                srcl0[c] = cN0 * phi0;
+                alpl0[c] = kk0 * phi0;
+                r0[c] = (v0.x + srcl0[c]) * rcp_fast(v0.y + alpl0[c]);
+              }
+            initm = 0;
+          }
+          // straight-line part: C independent dependency chains, no branches
+          double srcl1[C], alpl1[C], r1[C], xp[C], dtau[C], theomax[C], alp0[C], alp1[C];
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            const double u1 = (dnu[c] - nudv1) * inv_aa;
+            const double phi1 = norm * exp_neg(-(u1 * u1));
+            srcl1[c] = cN1 * phi1;
+            alpl1[c] = kk1 * phi1;
+          }
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            const double src0 = v0.x + srcl0[c], src1 = v1.x + srcl1[c];
+            alp0[c] = v0.y + alpl0[c];
+            alp1[c] = v1.y + alpl1[c];
+            dtau[c] = hds * (alp0[c] + alp1[c]);
+            theomax[c] = hds * (src0 + src1);
+            r1[c] = src1 * rcp_fast(alp1[c]);
+            xp[c] = exp_neg(-dtau[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            // transfer.F:1529-1541: S = j/alpha at each end, falling back to the other end
+            const double s_a = (alp0[c] > 0.0) ? r0[c] : ((alp1[c] > 0.0) ? r1[c] : 0.0);
+            const double s_b = (alp1[c] > 0.0) ? r1[c] : ((alp0[c] > 0.0) ? r0[c] : 0.0);
+            // transfer.F:1517-1527
+            const bool thick = dtau[c] > 1.e-6;
+            const double e0 = 1.0 - xp[c];
+            const double e1 = dtau[c] - e0;
+            const double bt = e1 * rcp_fast(dtau[c]);
+            const double b = thick ? bt : 0.5 * dtau[c];
+            const double a = thick ? (e0 - bt) : 0.5 * dtau[c];
+            const double x = thick ? xp[c] : (1.0 - dtau[c]);
+            double qv = (dtau[c] > (double)1e-9f) ? (a * s_a + b * s_b) : theomax[c];
+            qv = fmin(qv, theomax[c]);
+            const bool take = !((donem >> c) & 1);
+            inten[c] = take ? (inten[c] * x + qv) : inten[c];
+            srcl0[c] = take ? srcl1[c] : srcl0[c];
+            alpl0[c] = take ? alpl1[c] : alpl0[c];
+            r0[c] = take ? r1[c] : r0[c];
+            if (take && act[c] && alpl1[c] * ds < (double)(-0.01f)) maser = 1;  // telescope.F:4295
+          }
+          nelem += (unsigned)(nact - __popc(donem));
+          v0 = v1;
+          dvmu0 = dvmu1;
+          lw0 = lw1;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++)
+        if (act[c]) {
+          Iout[ch[c]] = inten[c];
+          if (mout) mout[ch[c]] = msk[c] ? 1 : 2;
+        }
+      nseg = (unsigned long long)(n1 > n0 ? n1 - n0 - 1 : 0) * nact;
+      nrc = nact;
+    }
     if (maser) atomicOr(&P.maser[l], 1);
-    nseg = (unsigned)(P.node_off[ray + 1] - P.node_off[ray]);
-    nseg = nseg > 0 ? nseg - 1 : 0;
   }
   // work counters
-  unsigned long long e = nelem, s = nseg, r = active ? 1 : 0;
   for (int o = 16; o; o >>= 1) {
-    e += __shfl_xor_sync(0xffffffffu, e, o);
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    r += __shfl_xor_sync(0xffffffffu, r, o);
+    nelem += __shfl_xor_sync(0xffffffffu, nelem, o);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, o);
+    nrc += __shfl_xor_sync(0xffffffffu, nrc, o);
   }
-  if (lane == 0 && r) {
-    atomicAdd(&P.counters[0], r);
-    atomicAdd(&P.counters[1], e);
-    atomicAdd(&P.counters[2], s);
+  if (lane == 0 && nrc) {
+    atomicAdd(&P.counters[0], nrc);
+    atomicAdd(&P.counters[1], nelem);
+    atomicAdd(&P.counters[2], nseg);
   }
 }
 
@@ -516,7 +754,6 @@ void launch_prep(const PrepParams &P, cudaStream_t st) {
   dim3 grid((unsigned)((P.ncell + 255) / 256), (unsigned)P.nl);
   prep_cells_kernel<<<grid, 256, 0, st>>>(P);
 }
-
 void launch_span(const RenderParams &P, cudaStream_t st) {
   const long long ntask = (long long)P.nl * P.nray;
   const long long threads = ntask * 32;
@@ -524,7 +761,13 @@ void launch_span(const RenderParams &P, cudaStream_t st) {
 }
 void launch_integrate(const RenderParams &P, unsigned total_items, cudaStream_t st) {
   if (!total_items) return;
-  integrate_kernel<<<(total_items + 127) / 128, 128, 0, st>>>(P, total_items);
+  const unsigned blocks = (total_items + 127) / 128;
+  switch (P.cpt) {
+    case 1: integrate_kernel<1><<<blocks, 128, 0, st>>>(P, total_items); break;
+    case 2: integrate_kernel<2><<<blocks, 128, 0, st>>>(P, total_items); break;
+    case 3: integrate_kernel<3><<<blocks, 128, 0, st>>>(P, total_items); break;
+    default: integrate_kernel<4><<<blocks, 128, 0, st>>>(P, total_items); break;
+  }
 }
 void launch_fill(const RenderParams &P, cudaStream_t st) {
   const long long ntask = (long long)P.nl * P.nray;

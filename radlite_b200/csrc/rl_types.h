@@ -13,6 +13,7 @@ constexpr int kRayAdpt = 4;
 constexpr int kRayRnpt = 4;
 constexpr int kMaxExtra = 40;  // 2 + 4*RAYADPT*2 = 34 used
 constexpr int kLgNrMax = 31;   // line.F:4657-4661
+constexpr int kChanPerThread = 4;  // velocity channels one thread of integrate_kernel carries
 
 // node flags (low 2 bits = tr_icross: 1 = R crossing, 2 = theta crossing, 3 = extra point)
 constexpr uint32_t kFlagIcrMask = 3u;
@@ -33,15 +34,22 @@ struct GridDev {
 // Per-line per-cell fields, one 32-byte record: {src_dust, alp_dust, N_up, N_down}
 // Cell index = (ir-1)*nth + (it-1): the Fortran (it,ir) order.
 
-// Node lists of all rays, structure of arrays, ray r owns [node_off[r], node_off[r+1]).
+// Node lists of all rays: one 64-byte record per node, ray r owns [node_off[r], node_off[r+1]).
+// The record is read as four 16-byte loads; all lanes working on the same ray read the same
+// address (broadcast), so an array of structures is the right layout here.
+constexpr int kCellFlagShift = 27;                 // cells.x = cell(t0,r0) | flags << 27
+constexpr int kCellMask = (1 << kCellFlagShift) - 1;
+struct __align__(16) NodeRec {
+  double ds;    // segment length to the previous node (vacuum rule applied); 0 for a ray's first node
+  double dvmu;  // Omega.v/c at the node (line independent)
+  double lw;    // interpolated line width [km/s]
+  double q;     // |dvmu - dvmu_prev| / (0.5 (lw+lw_prev)/c): the sub-grid trigger of line.F:4706-4709
+  double wr;    // dr
+  double wt;    // dt
+  int4 cells;   // cells (t0,r0)|flags<<27, (t1,r0), (t0,r1), (t1,r1)
+};
 struct NodesDev {
-  double *ds;    // segment length to the previous node (vacuum rule applied); 0 for a ray's first node
-  double *dvmu;  // Omega.v/c at the node (line independent)
-  double *lw;    // interpolated line width [km/s]
-  double *wr;    // dr
-  double *wt;    // dt
-  int4 *cell;    // cells (t0,r0), (t1,r0), (t0,r1), (t1,r1)
-  uint32_t *flag;
+  NodeRec *rec;
 };
 
 struct GeomParams {
@@ -76,6 +84,7 @@ struct RenderParams {
   int nl;    // lines in this batch
   int nfr;
   int subgrid, nonredundant;
+  int cpt;  // velocity channels per integrate_kernel thread (1..4)
   double levthres;
   double aksmax_c;  // aksmax/2.99792458d5
   double starfract;  // (rstar/rbeam0)^2 for the centre ray
@@ -91,7 +100,7 @@ struct RenderParams {
   const double *isrf_line;   // [nl][nfr]
   // per task (line_local*nray + ray)
   int4 *rng;                 // {lo, hi, c0, ch0_in_range}
-  unsigned int *nitems;      // [ntask]
+  unsigned int *nitems;      // [ntask] threads of the task (kChanPerThread channels each)
   const unsigned int *item_off;  // [ntask+1]
   double *img;               // [nl][nrr+1][nphi][nfr]
   unsigned char *integ;      // [nl][nrow][nfr] 1 = channel was integrated with cmask=1
