@@ -21,7 +21,9 @@ namespace rl {
 void launch_geom(const GeomParams &P, bool count, cudaStream_t st);
 void launch_prep(const PrepParams &P, cudaStream_t st);
 void launch_span(const RenderParams &P, cudaStream_t st);
-void launch_integrate(const RenderParams &P, unsigned total_items, cudaStream_t st);
+void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st);
+void launch_plan(const RenderParams &P, cudaStream_t st);
+int tile_smem_limit();
 void launch_fill(const RenderParams &P, cudaStream_t st);
 void launch_center_replicate(const RenderParams &P, cudaStream_t st);
 void launch_flux(const RenderParams &P, const double *surf, double *ring, double dist2, double *flux,
@@ -68,7 +70,6 @@ struct rl_ctx {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   long long launches = 0;
-  int cpt = kChanPerThread;  // tunable through RADLITE_B200_CPT (1..4)
   // grid
   int nr = 0, nt = 0, nth = 0;
   std::vector<double> rc, tc;
@@ -125,7 +126,7 @@ struct rl_ctx {
   DevBuf<int> d_lev_up, d_lev_down, d_inudust;
   DevBuf<double> d_wgt, d_freq, d_ld_src, d_ld_alp;
   DevBuf<int4> d_rng;
-  DevBuf<unsigned int> d_nitems, d_item_off;
+  DevBuf<unsigned int> d_nitems, d_item_off, d_ncta, d_cta_off;
   DevBuf<unsigned char> d_scan_tmp;
   DevBuf<double> d_img, d_ring, d_flux, d_tau;
   DevBuf<unsigned char> d_integ, d_cmask_accum;
@@ -188,7 +189,6 @@ int rl_create(rl_ctx **out, int device) {
     return -6;
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
-  if (const char *e = getenv("RADLITE_B200_CPT")) c->cpt = std::max(1, std::min(4, atoi(e)));
   c->d_status.ensure(1);
   c->d_counters.ensure(3);
   cudaMemsetAsync(c->d_counters.p, 0, 3 * sizeof(unsigned long long), c->st);
@@ -670,6 +670,10 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
       L.dnu0 = nu1;
       L.ddnu = dnu;
       L.i_outer = 0.0;
+      L.k_aa = 3.33567e-6 * L.nu0;                    // line.F:2301
+      L.c_src = 5.27296241956e-28 * L.nu0 * L.aud;    // line.F:4571
+      L.c_alp = 5.27296241956e-28 * L.nu0;            // line.F:4584
+      L.inv_nu0 = 1.0 / L.nu0;
       if (c->out_itype == 2) {  // telescope.F:3996-4000
         const double f = c->linefreq[il];
         L.i_outer = 1.47455253991e-47 * (f * f * f) / (std::exp(4.7991598e-11 * f / kTempCmb) - 1.0);
@@ -727,6 +731,8 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     CU(c->d_rng.ensure(ntask));
     CU(c->d_nitems.ensure(ntask + 1));
     CU(c->d_item_off.ensure(ntask + 1));
+    CU(c->d_ncta.ensure((size_t)c->nray + 1));
+    CU(c->d_cta_off.ensure((size_t)c->nray + 1));
     CU(c->d_img.ensure((size_t)nb * nrow * nfr));
     CU(c->d_ring.ensure((size_t)nb * c->nrr * nfr));
     CU(c->d_flux.ensure((size_t)nl * nfr));
@@ -782,7 +788,6 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.nfr = nfr;
     P.subgrid = c->subgrid;
     P.nonredundant = c->nonredundant;
-    P.cpt = c->cpt;
     P.levthres = c->levthres;
     P.aksmax_c = aksmax / 2.99792458e5;
     {
@@ -802,6 +807,9 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.rng = c->d_rng.p;
     P.nitems = c->d_nitems.p;
     P.item_off = c->d_item_off.p;
+    P.ncta = c->d_ncta.p;
+    P.cta_off = c->d_cta_off.p;
+    P.smem_budget = tile_smem_limit();
     P.img = c->d_img.p;
     P.integ = want_mask ? c->d_integ.p : nullptr;
     P.tau_center = c->d_tau.p;
@@ -818,15 +826,25 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
                                        (int)(ntask + 1), c->st));
       c->launches++;
     }
-    unsigned total_items = 0;
-    CU(cudaMemcpyAsync(&total_items, c->d_item_off.p + ntask, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+    launch_plan(P, c->st);
+    c->launches++;
+    {
+      size_t tmp_bytes = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_ncta.p, c->d_cta_off.p, c->nray + 1, c->st);
+      CU(c->d_scan_tmp.ensure(tmp_bytes));
+      CU(cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, c->d_ncta.p, c->d_cta_off.p, c->nray + 1,
+                                       c->st));
+      c->launches++;
+    }
+    unsigned total_ctas = 0;
+    CU(cudaMemcpyAsync(&total_ctas, c->d_cta_off.p + c->nray, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
     CU(cudaEventRecord(c->ev[2], c->st));
     CU(cudaStreamSynchronize(c->st));
     // ---- ray integration ----
-    launch_integrate(P, total_items, c->st);
+    launch_integrate(P, total_ctas, c->st);
     CU(cudaEventRecord(c->ev[5], c->st));
     launch_fill(P, c->st);
-    c->launches += 2;
+    c->launches += 3;
     if (imcir) {
       launch_center_replicate(P, c->st);
       c->launches++;

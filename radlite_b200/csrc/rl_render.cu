@@ -7,11 +7,9 @@
 //   integrate_kernel    telescope.F:3889-4312 (charintline), line.F:4636-4848
 //                       (clever_integrate_element_linedust), line.F:4515-4624
 //                       (integrate_element_linedust), line.F:2280 (voigt_profile),
-//                       transfer.F:1498 (qdr_src_2).  One thread carries kChanPerThread velocity
-//                       channels of one (line, ray): the node record, the bilinear gather of the
-//                       per-line cell fields and the per-segment profile constants are computed
-//                       once and shared by the channels, which also gives the FP64 pipe
-//                       kChanPerThread independent dependency chains per thread.
+//                       transfer.F:1498 (qdr_src_2).  tile_kernel: one block = one ray x a tile of
+//                       (line, channel) items, node data staged in shared memory; center_kernel:
+//                       the centre ray (star mixing, char_tau_center).
 //   fill_kernel         telescope.F:582-612 continuum copy for the skipped channels
 //   ringsum/flux        telescope.F:1388-1433 (calc_freq_flux_observer), fixed summation order
 #include "rl_types.h"
@@ -138,12 +136,12 @@ __global__ void __launch_bounds__(256) span_kernel(RenderParams P) {
   const long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long ntask = (long long)P.nl * P.nray;
   if (task >= ntask) return;
-  const int l = (int)(task / P.nray), ray = (int)(task % P.nray);
+  const int ray = (int)(task / P.nl), l = (int)(task % P.nl);  // ray-major tasks
   if (ray == 0 || !P.nonredundant) {
     if (lane == 0) {
       P.rng[task] = make_int4(1, P.nfr - 1, -1, ray == 0 ? 2 : 1);
-      // the centre ray keeps one channel per thread (it also produces char_tau_center)
-      P.nitems[task] = ray == 0 ? P.nfr : (P.nfr + P.cpt - 1) / P.cpt;
+      // the centre ray is traced by center_kernel (it also produces char_tau_center)
+      P.nitems[task] = ray == 0 ? 0 : P.nfr;
     }
     return;
   }
@@ -197,7 +195,7 @@ __global__ void __launch_bounds__(256) span_kernel(RenderParams P) {
     }
     if (hi < lo) { lo = 1; hi = 0; }
     P.rng[task] = make_int4(lo, hi, c0i, ch0_out ? 0 : 1);
-    P.nitems[task] = (unsigned)((n + P.cpt - 1) / P.cpt);
+    P.nitems[task] = (unsigned)n;
   }
 }
 
@@ -383,244 +381,335 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return y;
 }
 
-// exp(x) for x <= 0, branch free: x = n ln2 + r, |r| <= ln2/2, degree-12 Taylor polynomial
-// (truncation 1.7e-16), 2^n through the exponent field; below -708 the result is flushed to 0.
-__device__ __forceinline__ double exp_neg(double x) {
-  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);  // 1.5*2^52: round to nearest
+// ------------------------------------------------------------------------------------------
+// tile_kernel: the formal solution for one ray x a tile of (line, channel) items.
+//
+// One thread block owns one camera ray and kTileThreads consecutive entries of the ray's item list
+// (all channels the reference integrates, lines in index order: "ray x line tile").  The ray's nodes
+// are processed in chunks: first the block cooperatively stages, for every (node, line of the tile),
+// the interpolated cell values and all per-segment constants of the line profile in shared memory
+// (one thread per pair, so this work is done once per ray, line and node instead of once per
+// channel); then every thread walks the chunk for its own channel, reading the staged values
+// (shared-memory broadcast within a line) and advancing I <- I e^{-dtau} + Q.  All threads of a
+// block walk the same ray, so there is no trip-count divergence; the only divergent paths are the
+// rare ones of the reference itself (velocity sub-gridding, re-initialisation in the inner hole).
+// ------------------------------------------------------------------------------------------
+struct __align__(16) StagedLine {  // per (node, line): 64 bytes
+  double srcd, alpd;   // dust source / opacity at the node (line.F:4058-4063)
+  double cN, kk;       // c_src N_up ; c_alp (N_down B_du - N_up B_ud)
+  double inv_aa, nudv; // 1/(k_aa * mean width of the segment ending here) ; nu0 * Omega.v/c
+  double A1, K1;       // cN, kk times the profile norm 0.5641.../aa of the segment ending here
+};
+struct __align__(16) StagedNode {  // per node: 48 bytes
+  double ds, dvmu, q, lwav;
+  uint32_t flags, pad0, pad1, pad2;
+};
+
+// exp(x) for x <= 0: x = (64 k + j) ln2/64 + r, |r| <= ln2/128; exp(r) by a degree-5 polynomial
+// (truncation 3.5e-17), 2^(j/64) from a 64-entry shared-memory table, 2^k through the exponent
+// field.  Branch free; results below exp(-700) are flushed to 0.  ~1 ulp, 10 FP64 instructions.
+__device__ __forceinline__ double exp_neg_tab(double x, const double *__restrict__ tab) {
+  const double t = fma(x, 92.332482616893656877, 6755399441055744.0);  // 64/ln2, 1.5*2^52
   const int n = __double2loint(t);
   const double fn = t - 6755399441055744.0;
-  double r = fma(fn, -6.93147180369123816490e-01, x);
-  r = fma(fn, -1.90821492927058770002e-10, r);
-  double p = 2.08767569878680989792e-09;              // 1/12!
-  p = fma(p, r, 2.50521083854417187751e-08);          // 1/11!
-  p = fma(p, r, 2.75573192239858906526e-07);          // 1/10!
-  p = fma(p, r, 2.75573192239858906526e-06);          // 1/9!
-  p = fma(p, r, 2.48015873015873015873e-05);          // 1/8!
-  p = fma(p, r, 1.98412698412698412698e-04);          // 1/7!
-  p = fma(p, r, 1.38888888888888888889e-03);          // 1/6!
-  p = fma(p, r, 8.33333333333333333333e-03);          // 1/5!
-  p = fma(p, r, 4.16666666666666666667e-02);          // 1/4!
-  p = fma(p, r, 1.66666666666666666667e-01);          // 1/3!
+  double r = fma(fn, -1.08304246932675596327e-02, x);   // ln2_hi/64 (ln2_hi has 32 trailing zero bits)
+  r = fma(fn, -2.98158582698529328128e-12, r);           // ln2_lo/64
+  double p = fma(r, 8.33333333333333333333e-03, 4.16666666666666666667e-02);
+  p = fma(p, r, 1.66666666666666666667e-01);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  const double scale = __hiloint2double((n + 1023) << 20, 0);
-  return (x < -708.0) ? 0.0 : p * scale;
+  const double tj = tab[n & 63];
+  const int hi = __double2hiint(tj) + ((n >> 6) << 20);
+  const double sc = __hiloint2double(hi, __double2loint(tj));
+  const bool tiny = (unsigned)__double2hiint(x) > 0xC085E000u;  // x < -700
+  return tiny ? 0.0 : p * sc;
 }
 
-// ------------------------------------------------------------------------------------------
-// integrate_kernel: one thread = (line, ray, up to kChanPerThread channels)
-// ------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(128) integrate_kernel(RenderParams P, unsigned total_threads) {
-  const unsigned item = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const long long ntask = (long long)P.nl * P.nray;
-  const bool active = item < total_threads;
-  // the warp's first work item -> task by binary search; later lanes walk forward
-  const unsigned first = __shfl_sync(0xffffffffu, item, 0);
-  long long task = 0;
-  if (lane == 0 && first < total_threads) {
-    long long lo = 0, hi = ntask;  // largest t with item_off[t] <= first
+// sub-gridded segment in the staged (cN, kk) form (line.F:4745-4833); reference-ordered arithmetic
+__device__ __noinline__ int subgrid_tile(const LineDev &L, double dnu_ch, double &inten, double ds,
+                                         double sleft, double sright, double sd0, double ad0,
+                                         double cN0, double kk0, double dv0, double sd1, double ad1,
+                                         double cN1, double kk1, double dv1, double lw, double &srcl0,
+                                         double &alpl0, int init) {
+  const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
+  const double aa = 3.33567e-6 * L.nu0 * (0.5 * (lw + lw));
+  const double norm = 0.56419583546 / aa;
+  double sp = 0.0, cN_p = cN0, kk_p = kk0, dv_p = dv0, sd_p = sd0, ad_p = ad0;
+  int n = 0;
+  for (int j = 1; j <= kLgNrMax + 1; j++) {
+    double s, cN_c, kk_c, dv_c, sd_c, ad_c;
+    if (j <= kLgNrMax) {
+      s = sleft + (j - 1) * lg_ds;
+      if (!(s > 0.0 && s < ds)) continue;
+      const double eps = s / ds, epsp = 1.0 - eps;
+      cN_c = epsp * cN0 + eps * cN1;
+      kk_c = epsp * kk0 + eps * kk1;
+      dv_c = epsp * dv0 + eps * dv1;
+      sd_c = epsp * sd0 + eps * sd1;
+      ad_c = epsp * ad0 + eps * ad1;
+    } else {
+      s = ds; cN_c = cN1; kk_c = kk1; dv_c = dv1; sd_c = sd1; ad_c = ad1;
+    }
+    if (init) {
+      const double u0 = (dnu_ch - L.nu0 * dv_p) / aa;
+      const double phi0 = norm * exp(-(u0 * u0));
+      srcl0 = cN_p * phi0;
+      alpl0 = kk_p * phi0;
+      init = 0;
+    }
+    const double u1 = (dnu_ch - L.nu0 * dv_c) / aa;
+    const double phi1 = norm * exp(-(u1 * u1));
+    const double srcl1 = cN_c * phi1, alpl1 = kk_c * phi1;
+    inten = qdr_src_2(inten, sd_p + srcl0, ad_p + alpl0, sd_c + srcl1, ad_c + alpl1, s - sp);
+    srcl0 = srcl1;
+    alpl0 = alpl1;
+    n++;
+    sp = s; cN_p = cN_c; kk_p = kk_c; dv_p = dv_c; sd_p = sd_c; ad_p = ad_c;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 4) tile_kernel(RenderParams P) {
+  extern __shared__ double4 smem_raw[];
+  __shared__ double s_exptab[64];
+  __shared__ int s_ray, s_l0, s_l1;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 64) s_exptab[tid] = exp2((double)tid * (1.0 / 64.0));
+  if (tid == 0) {
+    // which ray does this block belong to: largest r with cta_off[r] <= blockIdx.x
+    int lo = 0, hi = P.nray;
     while (hi - lo > 1) {
-      const long long mid = (lo + hi) >> 1;
-      if (P.item_off[mid] <= first) lo = mid;
+      const int mid = (lo + hi) >> 1;
+      if (P.cta_off[mid] <= blockIdx.x) lo = mid;
       else hi = mid;
     }
-    task = lo;
-  }
-  task = __shfl_sync(0xffffffffu, task, 0);
-  unsigned long long nelem = 0, nseg = 0, nrc = 0;
-  int maser = 0;
-  if (active) {
-    while (P.item_off[task + 1] <= item) task++;
-    const int l = (int)(task / P.nray), ray = (int)(task % P.nray);
-    const int k = (int)(item - P.item_off[task]);
-    const int4 rg = P.rng[task];
-    const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
-    double *__restrict__ Iout = P.img + row * P.nfr;
-    unsigned char *mout = P.integ ? P.integ + row * P.nfr : nullptr;
-    const long long n0 = P.node_off[ray], n1 = P.node_off[ray + 1];
-    if (ray == 0) {
-      // centre ray: one channel per thread, reference-ordered path (star mixing + char_tau_center)
-      double tau;
-      unsigned ne;
-      const double inten = integrate_ray_channel(P, l, 0, k, tau, ne, maser);
-      Iout[k] = inten;
-      if (mout) mout[k] = 2;
-      if (k == P.nfr - 1) P.tau_center[l] = tau;
-      nelem = ne;
-      nseg = (unsigned long long)(n1 - n0 - 1);
-      nrc = 1;
-    } else {
-      const LineDev L = P.lines[l];
-      const double4 *__restrict__ cellL = P.cellL + (size_t)l * P.ncell;
-      const int nch = task_nchan(P, rg);
-      int ch[C];
-      bool act[C], msk[C];
-      double dnu[C], inten[C], srcl0[C], alpl0[C], r0[C];
-      int nact = 0;
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        const int j = k * C + c;
-        act[c] = j < nch;
-        msk[c] = false;
-        ch[c] = act[c] ? task_chan(P, rg, j, msk[c]) : 0;
-        dnu[c] = P.line_dnu[(size_t)l * P.nfr + ch[c]];
-        inten[c] = (P.out_itype == 3) ? P.isrf_line[(size_t)l * P.nfr + ch[c]] : L.i_outer;
-        srcl0[c] = alpl0[c] = r0[c] = 0.0;
-        nact += act[c] ? 1 : 0;
-      }
-      // per-line constants of line.F:4571-4588 and 2301-2302
-      const double k_aa = 3.33567e-6 * L.nu0;
-      const double c_src = 5.27296241956e-28 * L.nu0 * L.aud;
-      const double c_alp = 5.27296241956e-28 * L.nu0;
-      const double inv_nu0 = 1.0 / L.nu0;
-      unsigned initm = (1u << C) - 1u;  // channels whose carried line terms must be (re)computed
-      if (n1 > n0 + 1) {
-        Node nd = load_node(P.nodes.rec, n0);
-        double4 v0 = gather_line(cellL, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
-        double dvmu0 = nd.dvmu, lw0 = nd.lw;
-        // software pipeline: the record of node i+2 and the gathered cell values of node i+1 are
-        // in flight while segment (i-1, i) is integrated
-        const long long last = n1 - 1;
-        Node na = load_node(P.nodes.rec, n0 + 1);
-        double4 va = gather_line(cellL, na.cells, na.wr, na.wt, na.flags & kFlagIcrMask);
-        Node nb = load_node(P.nodes.rec, min(n0 + 2, last));
-        for (long long i = n0 + 1; i < n1; i++) {
-          nd = na;
-          const double4 v1 = va;
-          na = nb;
-          va = gather_line(cellL, na.cells, na.wr, na.wt, na.flags & kFlagIcrMask);
-          nb = load_node(P.nodes.rec, min(i + 2, last));
-          const uint32_t fl = nd.flags;
-          const double ds = nd.ds, dvmu1 = nd.dvmu, lw1 = nd.lw;
-          // per-segment quantities shared by the channels
-          const double lwav = 0.5 * (lw0 + lw1);
-          const double inv_aa = 1.0 / (k_aa * lwav);
-          const double norm = 0.56419583546 * inv_aa;
-          const double cN1 = c_src * v1.z;
-          const double kk1 = c_alp * (v1.w * L.bdu - v1.z * L.bud);
-          const double nudv1 = L.nu0 * dvmu1;
-          const double hds = 0.5 * ds;
-          if (fl & (kFlagInit | kFlagStar | kFlagZero)) {
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-              if (fl & kFlagZero) inten[c] = 0.0;
-              if (fl & kFlagStar)
-                inten[c] = (1.0 - P.starfract) * inten[c] + P.starfract * P.star_line[(size_t)l * P.nfr + ch[c]];
-            }
-            initm = (1u << C) - 1u;
-          }
-          unsigned donem = 0;  // channels handled by the sub-grid path in this segment
-          if (P.subgrid && (2.0 * 3.0 * nd.q > 1.0)) {  // line.F:4715 (rare)
-            const double inv_dd = 1.0 / (dvmu1 - dvmu0);
-            const double dls3 = 3.0 * (ds / nd.q);
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-              const double s_c = ds * (dnu[c] * inv_nu0 - dvmu0) * inv_dd;
-              const double sright = s_c + dls3, sleft = s_c - dls3;
-              if (act[c] && sright > 0.0 && sleft < ds) {
-                Carry kc;
-                kc.srcl0 = srcl0[c];
-                kc.alpl0 = alpl0[c];
-                kc.init = (initm >> c) & 1;
-                double tau = 0.0;
-                nelem += subgrid_segment(L, dnu[c], inten[c], ds, sleft, sright, v0, v1, dvmu0, dvmu1,
-                                         lwav, kc, tau);
-                srcl0[c] = kc.srcl0;
-                alpl0[c] = kc.alpl0;
-                r0[c] = (v1.x + kc.srcl0) * rcp_fast(v1.y + kc.alpl0);
-                initm &= ~(1u << c);
-                donem |= 1u << c;
-                if (kc.alpl0 * ds < (double)(-0.01f)) maser = 1;
-              }
-            }
-          }
-          if (initm) {  // first segment of the ray / after the inner hole (rare)
-            const double cN0 = c_src * v0.z;
-            const double kk0 = c_alp * (v0.w * L.bdu - v0.z * L.bud);
-            const double nudv0 = L.nu0 * dvmu0;
-#pragma unroll
-            for (int c = 0; c < C; c++)
-              if ((initm >> c) & 1) {
-                const double u0 = (dnu[c] - nudv0) * inv_aa;
-                const double phi0 = norm * exp_neg(-(u0 * u0));
-                srcl0[c] = cN0 * phi0;
-                alpl0[c] = kk0 * phi0;
-                r0[c] = (v0.x + srcl0[c]) * rcp_fast(v0.y + alpl0[c]);
-              }
-            initm = 0;
-          }
-          // straight-line part: C independent dependency chains, no branches
-          double srcl1[C], alpl1[C], r1[C], xp[C], dtau[C], theomax[C], alp0[C], alp1[C];
-#pragma unroll
-          for (int c = 0; c < C; c++) {
-            const double u1 = (dnu[c] - nudv1) * inv_aa;
-            const double phi1 = norm * exp_neg(-(u1 * u1));
-            srcl1[c] = cN1 * phi1;
-            alpl1[c] = kk1 * phi1;
-          }
-#pragma unroll
-          for (int c = 0; c < C; c++) {
-            const double src0 = v0.x + srcl0[c], src1 = v1.x + srcl1[c];
-            alp0[c] = v0.y + alpl0[c];
-            alp1[c] = v1.y + alpl1[c];
-            dtau[c] = hds * (alp0[c] + alp1[c]);
-            theomax[c] = hds * (src0 + src1);
-            r1[c] = src1 * rcp_fast(alp1[c]);
-            xp[c] = exp_neg(-dtau[c]);
-          }
-#pragma unroll
-          for (int c = 0; c < C; c++) {
-            // transfer.F:1529-1541: S = j/alpha at each end, falling back to the other end
-            const double s_a = (alp0[c] > 0.0) ? r0[c] : ((alp1[c] > 0.0) ? r1[c] : 0.0);
-            const double s_b = (alp1[c] > 0.0) ? r1[c] : ((alp0[c] > 0.0) ? r0[c] : 0.0);
-            // transfer.F:1517-1527
-            const bool thick = dtau[c] > 1.e-6;
-            const double e0 = 1.0 - xp[c];
-            const double e1 = dtau[c] - e0;
-            const double bt = e1 * rcp_fast(dtau[c]);
-            const double b = thick ? bt : 0.5 * dtau[c];
-            const double a = thick ? (e0 - bt) : 0.5 * dtau[c];
-            const double x = thick ? xp[c] : (1.0 - dtau[c]);
-            double qv = (dtau[c] > (double)1e-9f) ? (a * s_a + b * s_b) : theomax[c];
-            qv = fmin(qv, theomax[c]);
-            const bool take = !((donem >> c) & 1);
-            inten[c] = take ? (inten[c] * x + qv) : inten[c];
-            srcl0[c] = take ? srcl1[c] : srcl0[c];
-            alpl0[c] = take ? alpl1[c] : alpl0[c];
-            r0[c] = take ? r1[c] : r0[c];
-            if (take && act[c] && alpl1[c] * ds < (double)(-0.01f)) maser = 1;  // telescope.F:4295
-          }
-          nelem += (unsigned)(nact - __popc(donem));
-          v0 = v1;
-          dvmu0 = dvmu1;
-          lw0 = lw1;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < C; c++)
-        if (act[c]) {
-          Iout[ch[c]] = inten[c];
-          if (mout) mout[ch[c]] = msk[c] ? 1 : 2;
-        }
-      nseg = (unsigned long long)(n1 > n0 ? n1 - n0 - 1 : 0) * nact;
-      nrc = nact;
+    s_ray = lo;
+    const unsigned *off = P.item_off + (size_t)lo * P.nl;
+    const unsigned base = off[0], M = off[P.nl] - base;
+    const unsigned g0 = (blockIdx.x - P.cta_off[lo]) * kTileThreads;
+    const unsigned g1 = min(g0 + kTileThreads, M) - 1;
+    // lines of the first and last item: largest l with off[l]-base <= g
+    int a = 0, b = P.nl;
+    while (b - a > 1) {
+      const int mid = (a + b) >> 1;
+      if (off[mid] - base <= g0) a = mid;
+      else b = mid;
     }
+    s_l0 = a;
+    b = P.nl;
+    while (b - a > 1) {
+      const int mid = (a + b) >> 1;
+      if (off[mid] - base <= g1) a = mid;
+      else b = mid;
+    }
+    s_l1 = a;
+  }
+  __syncthreads();
+  const int ray = s_ray, l0 = s_l0, nlc = s_l1 - s_l0 + 1;
+  const unsigned *off = P.item_off + (size_t)ray * P.nl;
+  const unsigned base = off[0], M = off[P.nl] - base;
+  const unsigned my = (blockIdx.x - P.cta_off[ray]) * kTileThreads + tid;
+  const bool active = my < M;
+  // my line and channel
+  int l = l0;
+  if (active) {
+    int a = l0, b = s_l1 + 1;
+    while (b - a > 1) {
+      const int mid = (a + b) >> 1;
+      if (off[mid] - base <= my) a = mid;
+      else b = mid;
+    }
+    l = a;
+  }
+  const int ml = l - l0;
+  const long long task = (long long)ray * P.nl + l;
+  const int4 rg = P.rng[task];
+  bool masked = false;
+  const int ch = active ? task_chan(P, rg, (int)(my - (off[l] - base)), masked) : 0;
+  const LineDev L = P.lines[l];
+  const double dnu = P.line_dnu[(size_t)l * P.nfr + ch];
+  double inten = (P.out_itype == 3) ? P.isrf_line[(size_t)l * P.nfr + ch] : L.i_outer;
+  const long long n0 = P.node_off[ray];
+  const int N = (int)(P.node_off[ray + 1] - n0);
+  // shared-memory carve-up: StagedNode[nch+1] then StagedLine[(nch+1)*nlc]
+  int nch = (P.smem_budget - (int)sizeof(StagedNode)) / (int)(nlc * sizeof(StagedLine) + sizeof(StagedNode)) - 1;
+  nch = max(1, min(kTileChunk, nch));
+  StagedNode *sn = reinterpret_cast<StagedNode *>(smem_raw);
+  StagedLine *sl = reinterpret_cast<StagedLine *>(sn + (nch + 1));
+  double src0 = 0.0, alp0 = 0.0, r0 = 0.0;
+  int init = 1, maser = 0;
+  unsigned nelem = 0;
+  for (int c0 = 1; c0 < N; c0 += nch) {
+    const int cnt = min(nch, N - c0);
+    // ---- stage nodes c0-1 .. c0+cnt-1 (slot 0 = the previous node) ----
+    for (int p = tid; p < (cnt + 1) * nlc; p += kTileThreads) {
+      const int slot = p / nlc, m = p - slot * nlc;
+      const int node = c0 - 1 + slot;
+      const Node nd = load_node(P.nodes.rec, n0 + node);
+      const LineDev Lm = P.lines[l0 + m];
+      const double4 v = gather_line(P.cellL + (size_t)(l0 + m) * P.ncell, nd.cells, nd.wr, nd.wt,
+                                    nd.flags & kFlagIcrMask);
+      const double lw_prev = (node > 0) ? __ldg(&P.nodes.rec[n0 + node - 1].lw) : nd.lw;
+      const double lwav = 0.5 * (lw_prev + nd.lw);
+      StagedLine s;
+      s.srcd = v.x;
+      s.alpd = v.y;
+      s.cN = Lm.c_src * v.z;
+      s.kk = Lm.c_alp * (v.w * Lm.bdu - v.z * Lm.bud);
+      s.inv_aa = 1.0 / (Lm.k_aa * lwav);
+      s.nudv = Lm.nu0 * nd.dvmu;
+      const double norm = 0.56419583546 * s.inv_aa;
+      s.A1 = s.cN * norm;
+      s.K1 = s.kk * norm;
+      sl[slot * nlc + m] = s;
+      if (m == 0) {
+        StagedNode t;
+        t.ds = nd.ds;
+        t.dvmu = nd.dvmu;
+        t.q = nd.q;
+        t.lwav = lwav;
+        t.flags = nd.flags;
+        t.pad0 = t.pad1 = t.pad2 = 0;
+        sn[slot] = t;
+      }
+    }
+    __syncthreads();
+    if (active) {
+      for (int slot = 1; slot <= cnt; slot++) {
+        const StagedNode ns = sn[slot];
+        const StagedLine s1 = sl[slot * nlc + ml];
+        const double ds = ns.ds, hds = 0.5 * ns.ds;
+        if (ns.flags & (kFlagInit | kFlagStar | kFlagZero)) {  // inner hole / inner boundary (rare)
+          if (ns.flags & kFlagZero) inten = 0.0;
+          if (ns.flags & kFlagStar)
+            inten = (1.0 - P.starfract) * inten + P.starfract * P.star_line[(size_t)l * P.nfr + ch];
+          init = 1;
+        }
+        if (P.subgrid && (2.0 * 3.0 * ns.q > 1.0)) {  // line.F:4715 (rare)
+          const double dvmu0 = sn[slot - 1].dvmu;
+          const double s_c = ds * (dnu * L.inv_nu0 - dvmu0) / (ns.dvmu - dvmu0);
+          const double dls3 = 3.0 * (ds / ns.q);
+          const double sright = s_c + dls3, sleft = s_c - dls3;
+          if (sright > 0.0 && sleft < ds) {
+            const StagedLine s0 = sl[(slot - 1) * nlc + ml];
+            double srcl0 = src0 - s0.srcd, alpl0 = alp0 - s0.alpd;
+            nelem += subgrid_tile(L, dnu, inten, ds, sleft, sright, s0.srcd, s0.alpd, s0.cN, s0.kk, dvmu0,
+                                  s1.srcd, s1.alpd, s1.cN, s1.kk, ns.dvmu, ns.lwav, srcl0, alpl0, init);
+            src0 = s1.srcd + srcl0;
+            alp0 = s1.alpd + alpl0;
+            r0 = src0 * rcp_fast(alp0);
+            init = 0;
+            if (alpl0 * ds < (double)(-0.01f)) maser = 1;
+            continue;
+          }
+        }
+        if (init) {  // first segment of the ray / after the inner hole (rare): line.F:4559-4586
+          const StagedLine s0 = sl[(slot - 1) * nlc + ml];
+          const double u0 = (dnu - s0.nudv) * s1.inv_aa;
+          const double phi0 = 0.56419583546 * s1.inv_aa * exp_neg_tab(-(u0 * u0), s_exptab);
+          src0 = s0.srcd + s0.cN * phi0;
+          alp0 = s0.alpd + s0.kk * phi0;
+          r0 = src0 * rcp_fast(alp0);
+          init = 0;
+        }
+        // line.F:4554-4597 + transfer.F:1498-1571, straight line
+        const double u1 = (dnu - s1.nudv) * s1.inv_aa;
+        const double e1g = exp_neg_tab(-(u1 * u1), s_exptab);
+        const double alpl1 = s1.K1 * e1g;
+        const double src1 = fma(s1.A1, e1g, s1.srcd);
+        const double alp1 = s1.alpd + alpl1;
+        const double dtau = hds * (alp0 + alp1);
+        const double theomax = hds * (src0 + src1);
+        const double r1 = src1 * rcp_fast(alp1);
+        const double xpe = exp_neg_tab(-fabs(dtau), s_exptab);
+        const bool p0 = alp0 > 0.0, p1 = alp1 > 0.0;
+        const double s_a = p0 ? r0 : (p1 ? r1 : 0.0);
+        const double s_b = p1 ? r1 : (p0 ? r0 : 0.0);
+        const bool thick = dtau > 1.e-6;
+        const double e0 = 1.0 - xpe;
+        const double ee1 = dtau - e0;
+        const double bt = ee1 * rcp_fast(dtau);
+        const double hb = 0.5 * dtau;
+        const double b = thick ? bt : hb;
+        const double a = thick ? (e0 - bt) : hb;
+        const double x = thick ? xpe : (1.0 - dtau);
+        double qv = (dtau > (double)1e-9f) ? fma(a, s_a, b * s_b) : theomax;
+        qv = fmin(qv, theomax);
+        inten = fma(inten, x, qv);
+        src0 = src1;
+        alp0 = alp1;
+        r0 = r1;
+        if (s1.K1 < 0.0 && alpl1 * ds < (double)(-0.01f)) maser = 1;  // telescope.F:4295
+        nelem++;
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
+    P.img[row * P.nfr + ch] = inten;
+    if (P.integ) P.integ[row * P.nfr + ch] = masked ? 1 : 2;
     if (maser) atomicOr(&P.maser[l], 1);
   }
   // work counters
+  unsigned long long e = nelem, s = active ? (unsigned long long)(N > 0 ? N - 1 : 0) : 0, r = active ? 1 : 0;
   for (int o = 16; o; o >>= 1) {
-    nelem += __shfl_xor_sync(0xffffffffu, nelem, o);
-    nseg += __shfl_xor_sync(0xffffffffu, nseg, o);
-    nrc += __shfl_xor_sync(0xffffffffu, nrc, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
   }
-  if (lane == 0 && nrc) {
-    atomicAdd(&P.counters[0], nrc);
-    atomicAdd(&P.counters[1], nelem);
-    atomicAdd(&P.counters[2], nseg);
+  if (lane == 0 && r) {
+    atomicAdd(&P.counters[0], r);
+    atomicAdd(&P.counters[1], e);
+    atomicAdd(&P.counters[2], s);
   }
+}
+
+// the centre ray (telescope.F:498-527): one thread per (line, channel), reference-ordered scalar
+// path; also yields char_tau_center
+__global__ void __launch_bounds__(128) center_kernel(RenderParams P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool active = i < P.nl * P.nfr;
+  unsigned long long e = 0, s = 0, r = 0;
+  if (active) {
+    const int l = i / P.nfr, ch = i % P.nfr;
+    double tau;
+    unsigned ne;
+    int maser = 0;
+    const double inten = integrate_ray_channel(P, l, 0, ch, tau, ne, maser);
+    const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi;
+    P.img[row * P.nfr + ch] = inten;
+    if (P.integ) P.integ[row * P.nfr + ch] = 2;
+    if (ch == P.nfr - 1) P.tau_center[l] = tau;
+    if (maser) atomicOr(&P.maser[l], 1);
+    e = ne;
+    s = (unsigned long long)(P.node_off[1] - P.node_off[0] - 1);
+    r = 1;
+  }
+  for (int o = 16; o; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  if (lane == 0 && r) {
+    atomicAdd(&P.counters[0], r);
+    atomicAdd(&P.counters[1], e);
+    atomicAdd(&P.counters[2], s);
+  }
+}
+
+// thread blocks of tile_kernel per ray
+__global__ void plan_kernel(RenderParams P) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray > P.nray) return;
+  unsigned n = 0;
+  if (ray < P.nray) {
+    const unsigned M = P.item_off[(size_t)(ray + 1) * P.nl] - P.item_off[(size_t)ray * P.nl];
+    n = (M + kTileThreads - 1) / kTileThreads;
+  }
+  P.ncta[ray] = n;
 }
 
 // continuum copy for the channels the reference skips (telescope.F:557-612); one warp per task
@@ -629,7 +718,7 @@ __global__ void __launch_bounds__(256) fill_kernel(RenderParams P) {
   const long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long ntask = (long long)P.nl * P.nray;
   if (task >= ntask) return;
-  const int l = (int)(task / P.nray), ray = (int)(task % P.nray);
+  const int ray = (int)(task / P.nl), l = (int)(task % P.nl);
   if (ray == 0 || !P.nonredundant) return;
   const int4 rg = P.rng[task];
   const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
@@ -759,15 +848,22 @@ void launch_span(const RenderParams &P, cudaStream_t st) {
   const long long threads = ntask * 32;
   span_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P);
 }
-void launch_integrate(const RenderParams &P, unsigned total_items, cudaStream_t st) {
-  if (!total_items) return;
-  const unsigned blocks = (total_items + 127) / 128;
-  switch (P.cpt) {
-    case 1: integrate_kernel<1><<<blocks, 128, 0, st>>>(P, total_items); break;
-    case 2: integrate_kernel<2><<<blocks, 128, 0, st>>>(P, total_items); break;
-    case 3: integrate_kernel<3><<<blocks, 128, 0, st>>>(P, total_items); break;
-    default: integrate_kernel<4><<<blocks, 128, 0, st>>>(P, total_items); break;
+void launch_plan(const RenderParams &P, cudaStream_t st) {
+  plan_kernel<<<(P.nray + 1 + 255) / 256, 256, 0, st>>>(P);
+}
+int tile_smem_limit() {
+  static int done = 0;
+  const int want = 44 * 1024;  // 4 blocks/SM of 128 threads stay resident
+  if (!done) {
+    cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    done = 1;
   }
+  return want;
+}
+void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
+  center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);
+  if (!total_ctas) return;
+  tile_kernel<<<total_ctas, kTileThreads, P.smem_budget, st>>>(P);
 }
 void launch_fill(const RenderParams &P, cudaStream_t st) {
   const long long ntask = (long long)P.nl * P.nray;

@@ -13,7 +13,8 @@ constexpr int kRayAdpt = 4;
 constexpr int kRayRnpt = 4;
 constexpr int kMaxExtra = 40;  // 2 + 4*RAYADPT*2 = 34 used
 constexpr int kLgNrMax = 31;   // line.F:4657-4661
-constexpr int kChanPerThread = 4;  // velocity channels one thread of integrate_kernel carries
+constexpr int kTileThreads = 128;  // threads (= ray-channel items) per tile_kernel block
+constexpr int kTileChunk = 32;     // nodes staged in shared memory per pass
 
 // node flags (low 2 bits = tr_icross: 1 = R crossing, 2 = theta crossing, 3 = extra point)
 constexpr uint32_t kFlagIcrMask = 3u;
@@ -76,6 +77,9 @@ struct LineDev {
   double dnu0;      // line_dnu(1)
   double ddnu;      // channel spacing dnu
   double i_outer;   // outer-BC start intensity for out_itype 0/2 (type 3: per channel array)
+  // derived constants (host): line.F:2301 aa = k_aa * width ; line.F:4571-4588 j_l = c_src N_up phi,
+  // alpha_l = c_alp (N_down B_du - N_up B_ud) phi
+  double k_aa, c_src, c_alp, inv_nu0;
 };
 
 struct RenderParams {
@@ -84,7 +88,6 @@ struct RenderParams {
   int nl;    // lines in this batch
   int nfr;
   int subgrid, nonredundant;
-  int cpt;  // velocity channels per integrate_kernel thread (1..4)
   double levthres;
   double aksmax_c;  // aksmax/2.99792458d5
   double starfract;  // (rstar/rbeam0)^2 for the centre ray
@@ -100,8 +103,12 @@ struct RenderParams {
   const double *isrf_line;   // [nl][nfr]
   // per task (line_local*nray + ray)
   int4 *rng;                 // {lo, hi, c0, ch0_in_range}
-  unsigned int *nitems;      // [ntask] threads of the task (kChanPerThread channels each)
-  const unsigned int *item_off;  // [ntask+1]
+  // tasks are ray-major: task = ray * nl + line_slot
+  unsigned int *nitems;      // [ntask+1] channels the reference integrates for the task
+  const unsigned int *item_off;  // [ntask+1] exclusive scan of nitems (ray-major item list)
+  unsigned int *ncta;        // [nray+1] thread blocks of tile_kernel per ray
+  const unsigned int *cta_off;   // [nray+1] exclusive scan of ncta
+  int smem_budget;           // dynamic shared memory per tile_kernel block [bytes]
   double *img;               // [nl][nrr+1][nphi][nfr]
   unsigned char *integ;      // [nl][nrow][nfr] 1 = channel was integrated with cmask=1
   double *tau_center;        // [nl]
