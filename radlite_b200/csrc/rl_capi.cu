@@ -23,7 +23,8 @@ void launch_prep(const PrepParams &P, cudaStream_t st);
 void launch_span(const RenderParams &P, cudaStream_t st);
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st);
 void launch_plan(const RenderParams &P, cudaStream_t st);
-int tile_smem_limit();
+int tile_smem_limit(int threads);
+int tile_max_lines(int threads);
 void launch_fill(const RenderParams &P, cudaStream_t st);
 void launch_center_replicate(const RenderParams &P, cudaStream_t st);
 void launch_flux(const RenderParams &P, const double *surf, double *ring, double dist2, double *flux,
@@ -126,6 +127,8 @@ struct rl_ctx {
   DevBuf<int> d_lev_up, d_lev_down, d_inudust;
   DevBuf<double> d_wgt, d_freq, d_ld_src, d_ld_alp;
   DevBuf<int4> d_rng;
+  DevBuf<CellMask> d_masks;
+  DevBuf<unsigned char> d_dense;
   DevBuf<unsigned int> d_nitems, d_item_off, d_ncta, d_cta_off;
   DevBuf<unsigned char> d_scan_tmp;
   DevBuf<double> d_img, d_ring, d_flux, d_tau;
@@ -635,6 +638,11 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
   int lb = (int)std::max(1.0, std::floor(6.0 * 1073741824.0 / per_line_bytes));
   lb = (int)std::min<double>(lb, std::floor(4.0e9 / ((double)c->nray * nfr)));
   lb = std::max(1, std::min(lb, nl));
+  // tile_kernel: 128-thread blocks when a ray carries enough (line, channel) items, else 64; a tile
+  // must hold two slots of all its lines in shared memory twice (double buffer)
+  const int tile_threads = (lb >= 16) ? 128 : 64;
+  lb = std::min(lb, tile_max_lines(tile_threads));
+  lb = std::min(lb, kSpanThreads);  // span_kernel: one thread and one mask bit per line
   if (want_mask) {
     const long long per = (long long)nrow * nfr;
     if (c->cmask_accum_n != per) {
@@ -674,6 +682,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
       L.c_src = 5.27296241956e-28 * L.nu0 * L.aud;    // line.F:4571
       L.c_alp = 5.27296241956e-28 * L.nu0;            // line.F:4584
       L.inv_nu0 = 1.0 / L.nu0;
+      L.kia = 614.9746732986623 / L.k_aa;  // sqrt(2^18/ln 2) / k_aa
       if (c->out_itype == 2) {  // telescope.F:3996-4000
         const double f = c->linefreq[il];
         L.i_outer = 1.47455253991e-47 * (f * f * f) / (std::exp(4.7991598e-11 * f / kTempCmb) - 1.0);
@@ -729,6 +738,12 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     const size_t ntask = (size_t)nb * c->nray;
     CU(c->d_cellL.ensure((size_t)nb * ncell));
     CU(c->d_rng.ensure(ntask));
+    CU(c->d_masks.ensure(ncell));
+    const bool sparse = !imcir && !want_mask;
+    if (sparse) {
+      CU(c->d_dense.ensure(ntask));
+      CU(cudaMemsetAsync(c->d_dense.p, 0, ntask, c->st));
+    }
     CU(c->d_nitems.ensure(ntask + 1));
     CU(c->d_item_off.ensure(ntask + 1));
     CU(c->d_ncta.ensure((size_t)c->nray + 1));
@@ -805,11 +820,15 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.star_line = c->d_star_line.p;
     P.isrf_line = c->d_isrf_line.p;
     P.rng = c->d_rng.p;
+    P.masks = c->d_masks.p;
+    P.sparse = sparse ? 1 : 0;
+    P.dense = sparse ? c->d_dense.p : nullptr;
     P.nitems = c->d_nitems.p;
     P.item_off = c->d_item_off.p;
     P.ncta = c->d_ncta.p;
     P.cta_off = c->d_cta_off.p;
-    P.smem_budget = tile_smem_limit();
+    P.tile_threads = tile_threads;
+    P.smem_budget = tile_smem_limit(tile_threads);
     P.img = c->d_img.p;
     P.integ = want_mask ? c->d_integ.p : nullptr;
     P.tau_center = c->d_tau.p;
@@ -817,7 +836,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.counters = c->d_counters.p;
     P.status = c->d_status.p;
     launch_span(P, c->st);
-    c->launches++;
+    c->launches += P.nonredundant ? 2 : 1;
     {
       size_t tmp_bytes = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_nitems.p, c->d_item_off.p, (int)(ntask + 1), c->st);
@@ -844,7 +863,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     launch_integrate(P, total_ctas, c->st);
     CU(cudaEventRecord(c->ev[5], c->st));
     launch_fill(P, c->st);
-    c->launches += 3;
+    c->launches += 2 + (P.nonredundant ? 1 : 0);
     if (imcir) {
       launch_center_replicate(P, c->st);
       c->launches++;

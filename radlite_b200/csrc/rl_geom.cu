@@ -225,16 +225,18 @@ __device__ void emit_node(const GeomParams &P, const Ray &R, Emit &E, long long 
     }
   }
   // sub-grid trigger of the segment ending here (line.F:4706-4709)
-  double q = 0.0;
+  double inv_lwav = 1.0 / lw;
   if (E.n > 0) {
     const double lwseg = 0.5 * (E.lw_prev + lw);
-    q = fabs((dvmu - E.dvmu_prev) / (lwseg / 2.99792458e5));
+    const double q = fabs((dvmu - E.dvmu_prev) / (lwseg / 2.99792458e5));
+    if (2.0 * 3.0 * q > 1.0) flag |= kFlagSub;
+    inv_lwav = 1.0 / lwseg;
   }
   NodeRec rec;
   rec.ds = ds;
   rec.dvmu = dvmu;
   rec.lw = lw;
-  rec.q = q;
+  rec.inv_lwav = inv_lwav;
   rec.wr = dr;
   rec.wt = dt;
   cells.x |= (int)(flag << kCellFlagShift);

@@ -27,7 +27,7 @@ __device__ __forceinline__ double4 ldg4(const double4 *p) {
 }
 
 struct Node {
-  double ds, dvmu, lw, q, wr, wt;
+  double ds, dvmu, lw, inv_lwav, wr, wt;
   int4 cells;
   uint32_t flags;
 };
@@ -40,7 +40,7 @@ __device__ __forceinline__ Node load_node(const NodeRec *__restrict__ rec, long 
   n.ds = a.x;
   n.dvmu = a.y;
   n.lw = b.x;
-  n.q = b.y;
+  n.inv_lwav = b.y;
   n.wr = c.x;
   n.wt = c.y;
   n.cells = d;
@@ -128,17 +128,48 @@ __global__ void __launch_bounds__(256) prep_cells_kernel(PrepParams P) {
 }
 
 // ------------------------------------------------------------------------------------------
-// velocity span of a ray for one line -> which channels the reference integrates
-// one warp per (line, ray)
+// velocity span of a ray for every line of the batch -> which channels the reference integrates
+//
+// minvel/maxvel of telescope.F:4265-4270 run over the start node of every segment whose
+// interpolated N_up + N_down exceeds LEVTHRES.  The interpolation weights are convex, so the test is
+// decided by the stencil cells alone whenever they agree: mask_kernel packs, per cell, one bit per
+// line "surely above" / "surely below" the threshold (128 lines = one uint4 each); span_kernel ANDs
+// the masks of a node's stencil cells and only evaluates the interpolation where they disagree.
+// One block per ray: threads first act as nodes (load the record, combine the masks, park them in
+// shared memory), then as lines (walk the parked nodes, min/max of Omega.v/c).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) span_kernel(RenderParams P) {
-  const int lane = threadIdx.x & 31;
-  const long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long ntask = (long long)P.nl * P.nray;
-  if (task >= ntask) return;
-  const int ray = (int)(task / P.nl), l = (int)(task % P.nl);  // ray-major tasks
+__global__ void __launch_bounds__(256) mask_kernel(RenderParams P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long cell = i >> 2;
+  const int w = (int)(i & 3);
+  if (cell >= P.ncell) return;
+  const double hi = P.levthres * (1.0 + 1.0e-9), lo = P.levthres * (1.0 - 1.0e-9);
+  uint32_t on = 0, off = 0;
+  for (int b = 0; b < 32; b++) {
+    const int l = 32 * w + b;
+    if (l < P.nl) {
+      const double2 zw = __ldg(reinterpret_cast<const double2 *>(P.cellL + (size_t)l * P.ncell + cell) + 1);
+      const double s = zw.x + zw.y;
+      on |= (s > hi ? 1u : 0u) << b;
+      off |= (s < lo ? 1u : 0u) << b;
+    }
+  }
+  reinterpret_cast<uint32_t *>(&P.masks[cell].on)[w] = on;
+  reinterpret_cast<uint32_t *>(&P.masks[cell].off)[w] = off;
+}
+
+__device__ __forceinline__ uint4 and4(uint4 a, uint4 b) {
+  return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
+}
+
+__global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
+  __shared__ double s_dv[kSpanThreads];
+  __shared__ uint32_t s_on[4][kSpanThreads], s_un[4][kSpanThreads];
+  const int ray = blockIdx.x, tid = threadIdx.x;
+  const int l = tid;  // the line this thread owns in the second phase
+  const long long task = (long long)ray * P.nl + l;
   if (ray == 0 || !P.nonredundant) {
-    if (lane == 0) {
+    if (l < P.nl) {
       P.rng[task] = make_int4(1, P.nfr - 1, -1, ray == 0 ? 2 : 1);
       // the centre ray is traced by center_kernel (it also produces char_tau_center)
       P.nitems[task] = ray == 0 ? 0 : P.nfr;
@@ -147,20 +178,56 @@ __global__ void __launch_bounds__(256) span_kernel(RenderParams P) {
   }
   const long long n0 = P.node_off[ray], n1 = P.node_off[ray + 1];
   const double4 *cellL = P.cellL + (size_t)l * P.ncell;
+  const int w = (l >> 5) & 3;
+  const uint32_t bit = 1u << (l & 31);
   double vmin = 2.0, vmax = -2.0;
   // telescope.F:4265-4270: start node of every segment, i.e. all nodes but the last
-  for (long long i = n0 + lane; i < n1 - 1; i += 32) {
-    const Node nd = load_node(P.nodes.rec, i);
-    const double4 v = gather_line(cellL, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
-    if (v.z + v.w > P.levthres) {
-      vmin = fmin(vmin, nd.dvmu);
-      vmax = fmax(vmax, nd.dvmu);
+  for (long long c = n0; c < n1 - 1; c += kSpanThreads) {
+    const int cnt = (int)min((long long)kSpanThreads, n1 - 1 - c);
+    if (tid < cnt) {
+      const Node nd = load_node(P.nodes.rec, c + tid);
+      const int icr = nd.flags & kFlagIcrMask;
+      const CellMask *mk = P.masks;
+      uint4 on = __ldg(&mk[nd.cells.x].on), off = __ldg(&mk[nd.cells.x].off);
+      if (icr != 2) {
+        on = and4(on, __ldg(&mk[nd.cells.y].on));
+        off = and4(off, __ldg(&mk[nd.cells.y].off));
+      }
+      if (icr != 1) {
+        on = and4(on, __ldg(&mk[nd.cells.z].on));
+        off = and4(off, __ldg(&mk[nd.cells.z].off));
+      }
+      if (icr == 3) {
+        on = and4(on, __ldg(&mk[nd.cells.w].on));
+        off = and4(off, __ldg(&mk[nd.cells.w].off));
+      }
+      s_dv[tid] = nd.dvmu;
+      s_on[0][tid] = on.x; s_on[1][tid] = on.y; s_on[2][tid] = on.z; s_on[3][tid] = on.w;
+      s_un[0][tid] = ~(on.x | off.x); s_un[1][tid] = ~(on.y | off.y);
+      s_un[2][tid] = ~(on.z | off.z); s_un[3][tid] = ~(on.w | off.w);
     }
+    __syncthreads();
+    if (l < P.nl) {
+      for (int t = 0; t < cnt; t++) {
+        const uint32_t o = s_on[w][t], u = s_un[w][t];
+        if ((o | u) & bit) {
+          bool in = (o & bit) != 0;
+          if (!in) {  // stencil cells disagree (or sit on the threshold): evaluate the interpolation
+            const Node nd = load_node(P.nodes.rec, c + t);
+            const double4 v = gather_line(cellL, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
+            in = v.z + v.w > P.levthres;
+          }
+          if (in) {
+            const double dv = s_dv[t];
+            vmin = fmin(vmin, dv);
+            vmax = fmax(vmax, dv);
+          }
+        }
+      }
+    }
+    __syncthreads();
   }
-  for (int o = 16; o; o >>= 1) {
-    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-  }
+  if (l >= P.nl) return;
   // REAL*4 minvel/maxvel (common_telescope.h:17), initial values 1 and -1 (telescope.F:388-391)
   const float minvel = (vmin < 1.0) ? (float)vmin : 1.0f;
   const float maxvel = (vmax > -1.0) ? (float)vmax : -1.0f;
@@ -169,34 +236,27 @@ __global__ void __launch_bounds__(256) span_kernel(RenderParams P) {
   const double *velo = P.velo + (size_t)l * P.nfr;
   // channel 0 (reference inu=1) is always integrated; 1..nfr-1 only inside [lo_lim, hi_lim]
   int lo = P.nfr, hi = -1, c0 = P.nfr;
-  for (int c = 1 + lane; c < P.nfr; c += 32) {
-    const double v = velo[c];
+  for (int ch = 1; ch < P.nfr; ch++) {
+    const double v = __ldg(&velo[ch]);
     const bool in = (v <= hi_lim) && (v >= lo_lim);
     if (in) {
-      lo = min(lo, c);
-      hi = max(hi, c);
+      lo = min(lo, ch);
+      hi = max(hi, ch);
     } else {
-      c0 = min(c0, c);
+      c0 = min(c0, ch);
     }
   }
-  for (int o = 16; o; o >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
+  const double v0 = velo[0];
+  const bool ch0_out = (v0 > hi_lim) || (v0 < lo_lim);  // telescope.F:550-551
+  int n = 1 + ((hi >= lo) ? (hi - lo + 1) : 0);
+  int c0i = -1;
+  if (!ch0_out && c0 < P.nfr) {  // continuum not known after channel 0: the first skipped channel is integrated
+    c0i = c0;
+    n++;
   }
-  if (lane == 0) {
-    const double v0 = velo[0];
-    const bool ch0_out = (v0 > hi_lim) || (v0 < lo_lim);  // telescope.F:550-551
-    int n = 1 + ((hi >= lo) ? (hi - lo + 1) : 0);
-    int c0i = -1;
-    if (!ch0_out && c0 < P.nfr) {  // continuum not known after channel 0: the first skipped channel is integrated
-      c0i = c0;
-      n++;
-    }
-    if (hi < lo) { lo = 1; hi = 0; }
-    P.rng[task] = make_int4(lo, hi, c0i, ch0_out ? 0 : 1);
-    P.nitems[task] = (unsigned)n;
-  }
+  if (hi < lo) { lo = 1; hi = 0; }
+  P.rng[task] = make_int4(lo, hi, c0i, ch0_out ? 0 : 1);
+  P.nitems[task] = (unsigned)n;
 }
 
 // number of channels the reference integrates for a task and the j-th of them
@@ -342,9 +402,10 @@ __device__ __noinline__ double integrate_ray_channel(const RenderParams &P, int 
       k.init = 1;
     }
     bool done = false;
-    if (P.subgrid && 2.0 * 3.0 * nd.q > 1.0) {  // line.F:4715
+    if (P.subgrid && (fl & kFlagSub)) {  // line.F:4706-4715 (trigger evaluated by geom_kernel)
+      const double q = fabs((dvmu1 - dvmu0) / (0.5 * (lw0 + lw1) / 2.99792458e5));
       const double s_c = ds * (velo_ch - dvmu0) / (dvmu1 - dvmu0);
-      const double dls = ds / nd.q;
+      const double dls = ds / q;
       const double sright = s_c + 3.0 * dls, sleft = s_c - 3.0 * dls;
       if (sright > 0.0 && sleft < ds) {
         nelem += subgrid_segment(L, dnu_ch, inten, ds, sleft, sright, v0, v1, dvmu0, dvmu1,
@@ -369,71 +430,153 @@ __device__ __forceinline__ long long img_row(const RenderParams &P, int ray) {
   return ray == 0 ? 0 : (long long)P.nphi + (ray - 1);
 }
 
-// reciprocal to ~1 ulp: hardware seed (2^-23) + two Newton steps.  Not correctly rounded; used
-// where the reference divides (source function j/alpha, e1/dtau) -- differences are O(1e-16).
-__device__ __forceinline__ double rcp_fast(double x) {
+// ------------------------------------------------------------------------------------------
+// tile_kernel: the formal solution for one ray x a tile of (line, channel) items.
+//
+// One thread block owns one camera ray and a tile of consecutive entries of the ray's item list
+// (all channels the reference integrates, lines in index order: "ray x line tile"), one item per
+// thread.  The ray's nodes
+// are processed in chunks through a double-buffered shared-memory stage: while the block integrates
+// chunk c, the same threads gather and interpolate the cell values of chunk c+1 and precompute, per
+// (node, line of the tile), every channel-independent constant of the line profile -- so that work
+// is done once per ray, line and node instead of once per channel, and its memory latency hides
+// behind the arithmetic of the current chunk.  One barrier per chunk.
+//
+// All threads of a block walk the same ray: no trip-count divergence.  The integration step is
+// three-way, decided by a warp vote (the same case split as transfer.F:1517,1542):
+//   * every lane has dtau <= 1e-9 (about 2/3 of all steps in disk atmospheres): I <- I (1-dtau) + theomax
+//   * otherwise the full qdr_src_2 step with e^-dtau and the source-function ratios
+//   * nodes flagged by the geometry (first segment, inner hole / star mixing, 6q > 1 sub-grid
+//     candidates) take a separate reference-ordered path.
+//
+// Arithmetic notes (all deviations from the reference are << the 1e-6 tolerance):
+//   exp(x), x <= 0: n = round(x 2^18/ln2), exp = 2^(n>>18) T1[(n>>9)&511] T2[n&511] (1 + r), with
+//   two 512-entry shared-memory tables and |r| <= ln2/2^19; (1 + r) = e^r to r^2/2 < 9e-13 for the
+//   line profile, 1 + r + r^2/2 for exp(-dtau).  The Gaussian argument is carried pre-scaled so
+//   that n and r fall out of two FMAs.  Profile values below
+//   exp(-345) are flushed to 0.  Divisions: hardware reciprocal seed + two Newton steps (< 2e-11).
+// ------------------------------------------------------------------------------------------
+constexpr double kExpMagic = 6755399441055744.0;       // 1.5 * 2^52
+constexpr double kLog2eS = 378193.8487987964;          // 2^18 / ln 2
+constexpr double kLn2S = 2.6441466543577014e-06;       // ln 2 / 2^18
+constexpr double kCnorm = 0.0009174293836097514;       // 0.56419583546 / sqrt(2^18 / ln 2)
+constexpr unsigned kHiUmax = 0x40c64f52u;              // hi word of sqrt(345 * 2^18/ln 2): exp(-345) ~ 1e-150
+constexpr unsigned kHiTauMax = 0x40859000u;            // hi word of 690.0
+constexpr double kAlpTiny = 1.0e-280;                  // alpha <= this is treated like alpha <= 0
+
+struct __align__(16) HotLine {  // per (node, line): read by every step
+  double srcd, alpd;  // dust source / opacity at the node (line.F:4058-4063)
+  double A1, K1;      // c_src N_up and c_alp (N_down B_du - N_up B_ud), times the profile norm of the
+                      // segment ending here
+  double ia, nv;      // scaled reciprocal Doppler width of that segment ; nu0 Omega.v/c times ia
+};
+struct __align__(16) ColdLine {  // per (node, line): flagged nodes only
+  double cN, kk;      // c_src N_up ; c_alp (N_down B_du - N_up B_ud)
+};
+struct __align__(16) HotNode {
+  double hds;         // ds / 2
+  uint32_t flags, pad;
+};
+struct __align__(16) ColdNode {
+  double ds, dvmu, lwav, pad;
+};
+// shared-window byte addresses of one stage buffer (32-bit: the hot loop steps them directly)
+struct TileBuf {
+  uint32_t hn, cn, hl, cl;
+};
+template <class T>
+__device__ __forceinline__ T *smem_ptr(uint32_t a) {
+  return reinterpret_cast<T *>(__cvta_shared_to_generic(a));
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+constexpr int kSlotBytes = (int)(sizeof(HotNode) + sizeof(ColdNode));
+constexpr int kPairBytes = (int)(sizeof(HotLine) + sizeof(ColdLine));
+
+// n/x: hardware reciprocal seed (MUFU.RCP64H, about 2^-9) and two Newton steps, the second fused
+// with the multiplication: relative error ~ seed^4 < 2e-11
+__device__ __forceinline__ double div_fast(double n, double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double q = n * y;
+  return fma(q, e, q);
 }
 
-// ------------------------------------------------------------------------------------------
-// tile_kernel: the formal solution for one ray x a tile of (line, channel) items.
-//
-// One thread block owns one camera ray and kTileThreads consecutive entries of the ray's item list
-// (all channels the reference integrates, lines in index order: "ray x line tile").  The ray's nodes
-// are processed in chunks: first the block cooperatively stages, for every (node, line of the tile),
-// the interpolated cell values and all per-segment constants of the line profile in shared memory
-// (one thread per pair, so this work is done once per ray, line and node instead of once per
-// channel); then every thread walks the chunk for its own channel, reading the staged values
-// (shared-memory broadcast within a line) and advancing I <- I e^{-dtau} + Q.  All threads of a
-// block walk the same ray, so there is no trip-count divergence; the only divergent paths are the
-// rare ones of the reference itself (velocity sub-gridding, re-initialisation in the inner hole).
-// ------------------------------------------------------------------------------------------
-struct __align__(16) StagedLine {  // per (node, line): 64 bytes
-  double srcd, alpd;   // dust source / opacity at the node (line.F:4058-4063)
-  double cN, kk;       // c_src N_up ; c_alp (N_down B_du - N_up B_ud)
-  double inv_aa, nudv; // 1/(k_aa * mean width of the segment ending here) ; nu0 * Omega.v/c
-  double A1, K1;       // cN, kk times the profile norm 0.5641.../aa of the segment ending here
-};
-struct __align__(16) StagedNode {  // per node: 48 bytes
-  double ds, dvmu, q, lwav;
-  uint32_t flags, pad0, pad1, pad2;
-};
-
-// exp(x) for x <= 0: x = (64 k + j) ln2/64 + r, |r| <= ln2/128; exp(r) by a degree-5 polynomial
-// (truncation 3.5e-17), 2^(j/64) from a 64-entry shared-memory table, 2^k through the exponent
-// field.  Branch free; results below exp(-700) are flushed to 0.  ~1 ulp, 10 FP64 instructions.
-__device__ __forceinline__ double exp_neg_tab(double x, const double *__restrict__ tab) {
-  const double t = fma(x, 92.332482616893656877, 6755399441055744.0);  // 64/ln2, 1.5*2^52
+// 2^(n / 2^18) e^r, r = rp ln2/2^18: the table part of exp (see header).  T1, T2 = shared-window
+// addresses of the two tables.  QUAD = false: e^r ~ 1 + r (relative error < 9e-13, the line profile);
+// QUAD = true: 1 + r + r^2/2 (full double precision: exp(-dtau) feeds the cancelling differences
+// e0 = 1 - xp, e1 = dtau - e0 of transfer.F:1519-1520, whose error is the absolute error of xp).
+template <bool QUAD>
+__device__ __forceinline__ double exp_tab(double t, double rp, uint32_t T1, uint32_t T2) {
   const int n = __double2loint(t);
-  const double fn = t - 6755399441055744.0;
-  double r = fma(fn, -1.08304246932675596327e-02, x);   // ln2_hi/64 (ln2_hi has 32 trailing zero bits)
-  r = fma(fn, -2.98158582698529328128e-12, r);           // ln2_lo/64
-  double p = fma(r, 8.33333333333333333333e-03, 4.16666666666666666667e-02);
-  p = fma(p, r, 1.66666666666666666667e-01);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const double tj = tab[n & 63];
-  const int hi = __double2hiint(tj) + ((n >> 6) << 20);
-  const double sc = __hiloint2double(hi, __double2loint(tj));
-  const bool tiny = (unsigned)__double2hiint(x) > 0xC085E000u;  // x < -700
-  return tiny ? 0.0 : p * sc;
+  const double2 w = lds_f64x2(T2 + ((n << 4) & 0x1ff0));
+  const double v = lds_f64(T1 + ((n >> 6) & 0xff8));
+  double inner;
+  if (QUAD) inner = fma(w.y * rp, fma(rp, 0.5 * kLn2S, 1.0), w.x);
+  else inner = fma(w.y, rp, w.x);
+  const int hi = __double2hiint(v) + ((n >> 18) << 20);
+  return __hiloint2double(hi, __double2loint(v)) * inner;
+}
+// exp(-u^2 ln2/2^18) for the pre-scaled argument u; exactly 0 beyond exp(-345)
+__device__ __forceinline__ double gauss_tab(double u, uint32_t T1, uint32_t T2) {
+  const double t = fma(-u, u, kExpMagic);
+  const double fn = t - kExpMagic;
+  const double rp = fma(-u, u, -fn);
+  const double e = exp_tab<false>(t, rp, T1, T2);
+  const bool far = ((unsigned)__double2hiint(u) & 0x7fffffffu) > kHiUmax;
+  return far ? 0.0 : e;
+}
+// exp(-d), d >= 0 (clamped at ~690; lanes with d < 0 get an unused finite value)
+__device__ __forceinline__ double expneg_tab(double d, uint32_t T1, uint32_t T2) {
+  const unsigned h = min((unsigned)__double2hiint(d), kHiTauMax);
+  const double dc = __hiloint2double((int)h, __double2loint(d));
+  const double t = fma(dc, -kLog2eS, kExpMagic);
+  const double fn = t - kExpMagic;
+  const double rp = fma(dc, -kLog2eS, -fn);
+  return exp_tab<true>(t, rp, T1, T2);
+}
+
+// the qdr_src_2 step (transfer.F:1498-1571) with all case selections branch free; r0 = src0/alp0
+// comes in, r1 = src1/alp1 goes out
+__device__ __forceinline__ void full_step(double &inten, double alp0, double r0, double src1, double alp1,
+                                          double &r1, double dtau, double theomax, uint32_t T1, uint32_t T2) {
+  r1 = div_fast(src1, alp1);
+  const double xpe = expneg_tab(dtau, T1, T2);
+  const double e0 = 1.0 - xpe;
+  const double ee1 = dtau - e0;
+  const double bt = div_fast(ee1, dtau);
+  const double hb = 0.5 * dtau;
+  const bool thick = dtau > 1.e-6;
+  const double b = thick ? bt : hb;
+  const double a = thick ? (e0 - bt) : hb;
+  const double x = thick ? xpe : (1.0 - dtau);
+  const bool p0 = alp0 > kAlpTiny, p1 = alp1 > kAlpTiny;
+  const double s_a = p0 ? r0 : (p1 ? r1 : 0.0);
+  const double s_b = p1 ? r1 : (p0 ? r0 : 0.0);
+  double qv = fma(a, s_a, b * s_b);
+  qv = (dtau > (double)1e-9f) ? fmin(qv, theomax) : theomax;
+  inten = fma(inten, x, qv);
 }
 
 // sub-gridded segment in the staged (cN, kk) form (line.F:4745-4833); reference-ordered arithmetic
-__device__ __noinline__ int subgrid_tile(const LineDev &L, double dnu_ch, double &inten, double ds,
-                                         double sleft, double sright, double sd0, double ad0,
-                                         double cN0, double kk0, double dv0, double sd1, double ad1,
-                                         double cN1, double kk1, double dv1, double lw, double &srcl0,
-                                         double &alpl0, int init) {
+__device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch, double &inten, double ds,
+                                         double sleft, double sright, double sd0, double ad0, double cN0,
+                                         double kk0, double dv0, double sd1, double ad1, double cN1,
+                                         double kk1, double dv1, double lw, double &srcl0, double &alpl0,
+                                         int init) {
   const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
-  const double aa = 3.33567e-6 * L.nu0 * (0.5 * (lw + lw));
+  const double aa = k_aa * (0.5 * (lw + lw));
   const double norm = 0.56419583546 / aa;
   double sp = 0.0, cN_p = cN0, kk_p = kk0, dv_p = dv0, sd_p = sd0, ad_p = ad0;
   int n = 0;
@@ -452,13 +595,13 @@ __device__ __noinline__ int subgrid_tile(const LineDev &L, double dnu_ch, double
       s = ds; cN_c = cN1; kk_c = kk1; dv_c = dv1; sd_c = sd1; ad_c = ad1;
     }
     if (init) {
-      const double u0 = (dnu_ch - L.nu0 * dv_p) / aa;
+      const double u0 = (dnu_ch - nu0 * dv_p) / aa;
       const double phi0 = norm * exp(-(u0 * u0));
       srcl0 = cN_p * phi0;
       alpl0 = kk_p * phi0;
       init = 0;
     }
-    const double u1 = (dnu_ch - L.nu0 * dv_c) / aa;
+    const double u1 = (dnu_ch - nu0 * dv_c) / aa;
     const double phi1 = norm * exp(-(u1 * u1));
     const double srcl1 = cN_c * phi1, alpl1 = kk_c * phi1;
     inten = qdr_src_2(inten, sd_p + srcl0, ad_p + alpl0, sd_c + srcl1, ad_c + alpl1, s - sp);
@@ -470,12 +613,256 @@ __device__ __noinline__ int subgrid_tile(const LineDev &L, double dnu_ch, double
   return n;
 }
 
-__global__ void __launch_bounds__(kTileThreads, 4) tile_kernel(RenderParams P) {
+// per-block tables and per-item metadata of tile_kernel (file scope: the out-of-line slow path uses
+// them too)
+__shared__ double s_T1[512];         // 2^(j/512)
+__shared__ double2 s_T2[512];        // {2^(j/2^18), 2^(j/2^18) ln2/2^18}
+__shared__ int2 s_meta[128];      // {line slot, channel | cmask bit} of the thread's item
+__shared__ unsigned s_flags[128]; // maser | extra elements << 8 of the thread's item
+__shared__ double s_dnu[128];     // line_dnu of the thread's item
+
+// per-item state of tile_kernel: kept in registers across the whole ray
+struct Item {
+  double inten, src0, alp0, r0;
+};
+
+// one flagged segment of one item (first segment, inner hole / star, sub-grid candidate), out of
+// line.  st = {inten, src0, alp0, r0} in/out; returns maser | extra_elements << 1
+__device__ __noinline__ unsigned slow_step(double *st, TileBuf B, int nlc, int slot, int l, int ml, int ch,
+                                           double dnu, const LineDev *__restrict__ lines,
+                                           const double *__restrict__ star_line, int nfr, double starfract) {
+  double inten = st[0], src0 = st[1], alp0 = st[2], r0;
+  unsigned ret = 0;
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1), T2 = (uint32_t)__cvta_generic_to_shared(s_T2);
+  const uint32_t fl = smem_ptr<HotNode>(B.hn)[slot].flags;
+  const ColdNode c1 = smem_ptr<ColdNode>(B.cn)[slot], c0 = smem_ptr<ColdNode>(B.cn)[slot - 1];
+  const HotLine h1 = smem_ptr<HotLine>(B.hl)[slot * nlc + ml], h0 = smem_ptr<HotLine>(B.hl)[(slot - 1) * nlc + ml];
+  const ColdLine k1 = smem_ptr<ColdLine>(B.cl)[slot * nlc + ml], k0 = smem_ptr<ColdLine>(B.cl)[(slot - 1) * nlc + ml];
+  const double nu0 = __ldg(&lines[l].nu0);
+  const double ds = c1.ds;
+  int init = 0;
+  if (fl & (kFlagInit | kFlagStar | kFlagZero)) {
+    if (fl & kFlagZero) inten = 0.0;
+    if (fl & kFlagStar) inten = (1.0 - starfract) * inten + starfract * star_line[(size_t)l * nfr + ch];
+    init = 1;
+  }
+  bool done = false;
+  if (fl & kFlagSub) {  // line.F:4706-4745
+    const double q = fabs((c1.dvmu - c0.dvmu) / (c1.lwav / 2.99792458e5));
+    const double s_c = ds * (dnu * __ldg(&lines[l].inv_nu0) - c0.dvmu) / (c1.dvmu - c0.dvmu);
+    const double dls3 = 3.0 * (ds / q);
+    const double sright = s_c + dls3, sleft = s_c - dls3;
+    if (sright > 0.0 && sleft < ds) {
+      double srcl0 = src0 - h0.srcd, alpl0 = alp0 - h0.alpd;
+      const int n = subgrid_tile(nu0, __ldg(&lines[l].k_aa), dnu, inten, ds, sleft, sright, h0.srcd, h0.alpd,
+                                 k0.cN, k0.kk, c0.dvmu, h1.srcd, h1.alpd, k1.cN, k1.kk, c1.dvmu, c1.lwav,
+                                 srcl0, alpl0, init);
+      src0 = h1.srcd + srcl0;
+      alp0 = h1.alpd + alpl0;
+      r0 = div_fast(src0, alp0);
+      if (alpl0 * ds < (double)(-0.01f)) ret |= 1u;
+      ret += (unsigned)(n - 1) << 1;
+      done = true;
+    }
+  }
+  if (!done) {
+    if (init) {  // line.F:4559-4586: the start point with this segment's width
+      const double u0 = fma(dnu, h1.ia, -((nu0 * c0.dvmu) * h1.ia));
+      const double phi0 = (kCnorm * h1.ia) * gauss_tab(u0, T1, T2);
+      src0 = h0.srcd + k0.cN * phi0;
+      alp0 = h0.alpd + k0.kk * phi0;
+    }
+    r0 = div_fast(src0, alp0);
+    const double u1 = fma(dnu, h1.ia, -h1.nv);
+    const double e = gauss_tab(u1, T1, T2);
+    const double alpl1 = h1.K1 * e;
+    const double src1 = fma(h1.A1, e, h1.srcd);
+    const double alp1 = h1.alpd + alpl1;
+    const double hds = 0.5 * ds;
+    const double dtau = hds * (alp0 + alp1), theomax = hds * (src0 + src1);
+    double r1;
+    full_step(inten, alp0, r0, src1, alp1, r1, dtau, theomax, T1, T2);
+    src0 = src1;
+    alp0 = alp1;
+    r0 = r1;
+    if (alpl1 * ds < (double)(-0.01f)) ret |= 1u;
+  }
+  st[0] = inten;
+  st[1] = src0;
+  st[2] = alp0;
+  st[3] = r0;
+  return ret;
+}
+template <int NT>
+__device__ __noinline__ void stage_chunk(const RenderParams &P, const TileBuf &B, int nlc, int l0,
+                                            long long n0, int c0, int cnt, int tid) {
+  const int npair = (cnt + 1) * nlc;
+  for (int p = tid; p < npair; p += NT) {
+    const int slot = p / nlc, m = p - slot * nlc;
+    const int node = c0 - 1 + slot;
+    const Node nd = load_node(P.nodes.rec, n0 + node);
+    const LineDev *Lm = P.lines + (l0 + m);
+    const double4 v = gather_line(P.cellL + (size_t)(l0 + m) * P.ncell, nd.cells, nd.wr, nd.wt,
+                                  nd.flags & kFlagIcrMask);
+    const double c_src = __ldg(&Lm->c_src), c_alp = __ldg(&Lm->c_alp), bud = __ldg(&Lm->bud),
+                 bdu = __ldg(&Lm->bdu), nu0 = __ldg(&Lm->nu0), kia = __ldg(&Lm->kia);
+    ColdLine c;
+    c.cN = c_src * v.z;
+    c.kk = c_alp * (v.w * bdu - v.z * bud);
+    HotLine h;
+    h.srcd = v.x;
+    h.alpd = v.y;
+    h.ia = nd.inv_lwav * kia;
+    h.nv = (nu0 * nd.dvmu) * h.ia;
+    const double norm = kCnorm * h.ia;
+    h.A1 = c.cN * norm;
+    h.K1 = c.kk * norm;
+    smem_ptr<HotLine>(B.hl)[p] = h;
+    smem_ptr<ColdLine>(B.cl)[p] = c;
+    if (m == 0) {
+      HotNode a;
+      a.hds = 0.5 * nd.ds;
+      uint32_t fl = nd.flags & ~kFlagIcrMask;
+      if (!P.subgrid) fl &= ~kFlagSub;
+      if (node == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
+      a.flags = fl;
+      a.pad = 0;
+      smem_ptr<HotNode>(B.hn)[slot] = a;
+      ColdNode b;
+      const double lw_prev = (node > 0) ? __ldg(&P.nodes.rec[n0 + node - 1].lw) : nd.lw;
+      b.ds = nd.ds;
+      b.dvmu = nd.dvmu;
+      b.lwav = 0.5 * (lw_prev + nd.lw);
+      b.pad = 0.0;
+      smem_ptr<ColdNode>(B.cn)[slot] = b;
+    }
+  }
+}
+
+// raw staged data of one slot for one item, and what the profile evaluation makes of it
+struct RawSlot {
+  double2 sa, ak, iv;  // HotLine
+  double hds;
+  uint32_t fl;
+};
+struct PreSlot {
+  double src1, alp1, alpl1, hds;
+  uint32_t fl;
+  bool k1neg;
+};
+__device__ __forceinline__ RawSlot raw_load(uint32_t an, uint32_t ah) {
+  RawSlot r;
+  unsigned long long fw;
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(r.hds), "=l"(fw) : "r"(an));
+  r.fl = (uint32_t)fw;
+  r.iv = lds_f64x2(ah + 32);
+  r.ak = lds_f64x2(ah + 16);
+  r.sa = lds_f64x2(ah);
+  return r;
+}
+// line.F:4554-4597 at the end point of the segment: profile, line + dust source and opacity
+__device__ __forceinline__ PreSlot pre_compute(const RawSlot &r, double dnu, uint32_t T1, uint32_t T2) {
+  PreSlot g;
+  const double u = fma(dnu, r.iv.x, -r.iv.y);
+  const double e = gauss_tab(u, T1, T2);
+  g.alpl1 = r.ak.y * e;
+  g.src1 = fma(r.ak.x, e, r.sa.x);
+  g.alp1 = r.sa.y + g.alpl1;
+  g.hds = r.hds;
+  g.fl = r.fl;
+  g.k1neg = __double2hiint(r.ak.y) < 0;
+  return g;
+}
+
+// the segments of one staged chunk for the thread's item, software pipelined two slots deep: while
+// the carried intensity is advanced over slot s, the profile of slot s+1 is evaluated (it does not
+// depend on the carried state) and the staged record of slot s+2 is in flight from shared memory.
+// Flagged nodes (rare) are handled by an out-of-line call between runs of the register-resident
+// loop; everything but the item state is re-materialised after such a call (manual live-range
+// splitting: nothing else is live across it).
+__device__ __forceinline__ void integrate_chunk(const RenderParams &P, const TileBuf B, int nlc, int cnt,
+                                                Item &it, int l0, bool &r0ok) {
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1), T2 = (uint32_t)__cvta_generic_to_shared(s_T2);
+  int slot = 1;
+  while (slot <= cnt) {
+    const uint32_t stride = (uint32_t)nlc * (uint32_t)sizeof(HotLine);
+    const double dnu = s_dnu[threadIdx.x];
+    const uint32_t aoff = (uint32_t)(s_meta[threadIdx.x].x - l0) * (uint32_t)sizeof(HotLine);
+    // slot indices beyond cnt are clamped to cnt: their values are never used
+    const int s1 = min(slot + 1, cnt);
+    PreSlot cur = pre_compute(raw_load(B.hn + (uint32_t)slot * (uint32_t)sizeof(HotNode),
+                                       B.hl + (uint32_t)slot * stride + aoff), dnu, T1, T2);
+    uint32_t an = B.hn + (uint32_t)s1 * (uint32_t)sizeof(HotNode), ah = B.hl + (uint32_t)s1 * stride + aoff;
+    RawSlot rawA = raw_load(an, ah), rawB;
+    PreSlot curB;
+    // one pipeline beat: fetch slot+2 into `rout`, evaluate the profile of slot+1 from `rin` into
+    // `pout`, advance the intensity over `slot` with `pin`.  Unrolled twice with the roles of the A
+    // and B registers swapped, so that nothing has to be moved between beats.
+#define RL_BEAT(pin, rin, pout, rout)                                                              \
+  {                                                                                                \
+    const bool more = slot + 2 <= cnt;                                                             \
+    an += more ? (uint32_t)sizeof(HotNode) : 0u;                                                   \
+    ah += more ? stride : 0u;                                                                      \
+    rout = raw_load(an, ah);                                                                       \
+    pout = pre_compute(rin, dnu, T1, T2);                                                          \
+    if (pin.fl) break; /* block-uniform: this node takes the out-of-line path */                   \
+    /* advance the intensity over slot (transfer.F:1498-1571) */                                   \
+    const double dtau = pin.hds * (it.alp0 + pin.alp1);                                            \
+    const double theo = pin.hds * (it.src0 + pin.src1);                                            \
+    /* inverted populations (K1 < 0) force the full path, which carries the maser test */          \
+    const bool work = (dtau > (double)1e-9f) | pin.k1neg;                                          \
+    if (!__any_sync(0xffffffffu, work)) {                                                          \
+      /* transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau */                                  \
+      it.inten = fma(it.inten, 1.0 - dtau, theo);                                                  \
+      r0ok = false;                                                                                \
+    } else {                                                                                       \
+      if (!r0ok) it.r0 = div_fast(it.src0, it.alp0);                                               \
+      double r1;                                                                                   \
+      full_step(it.inten, it.alp0, it.r0, pin.src1, pin.alp1, r1, dtau, theo, T1, T2);             \
+      it.r0 = r1;                                                                                  \
+      if (__any_sync(0xffffffffu, pin.k1neg)) { /* telescope.F:4295 */                             \
+        if (pin.alpl1 * (pin.hds + pin.hds) < (double)(-0.01f)) s_flags[threadIdx.x] |= 1u;        \
+      }                                                                                            \
+      r0ok = true;                                                                                 \
+    }                                                                                              \
+    it.src0 = pin.src1;                                                                            \
+    it.alp0 = pin.alp1;                                                                            \
+    slot++;                                                                                        \
+    if (slot > cnt) break;                                                                         \
+  }
+    for (;;) {
+      RL_BEAT(cur, rawA, curB, rawB)
+      RL_BEAT(curB, rawB, cur, rawA)
+    }
+#undef RL_BEAT
+    if (slot > cnt) break;
+    {
+      const int2 mt = s_meta[threadIdx.x];
+      double st[4] = {it.inten, it.src0, it.alp0, it.r0};
+      const unsigned f = slow_step(st, B, nlc, slot, mt.x, mt.x - l0, mt.y & 0x3fffffff, s_dnu[threadIdx.x],
+                                   P.lines, P.star_line, P.nfr, P.starfract);
+      it.inten = st[0];
+      it.src0 = st[1];
+      it.alp0 = st[2];
+      it.r0 = st[3];
+      if (f) s_flags[threadIdx.x] = (s_flags[threadIdx.x] | (f & 1u)) + ((f >> 1) << 8);
+      r0ok = true;
+      slot++;
+    }
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 640 / NT) tile_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ double4 smem_raw[];
-  __shared__ double s_exptab[64];
   __shared__ int s_ray, s_l0, s_l1;
+  __shared__ unsigned s_g0, s_g1, s_M;
   const int tid = threadIdx.x, lane = tid & 31;
-  if (tid < 64) s_exptab[tid] = exp2((double)tid * (1.0 / 64.0));
+  for (int j = tid; j < 512; j += NT) {
+    s_T1[j] = exp2((double)j * (1.0 / 512.0));
+    const double w = exp2((double)j * (1.0 / 262144.0));
+    s_T2[j] = make_double2(w, w * kLn2S);
+  }
   if (tid == 0) {
     // which ray does this block belong to: largest r with cta_off[r] <= blockIdx.x
     int lo = 0, hi = P.nray;
@@ -487,173 +874,99 @@ __global__ void __launch_bounds__(kTileThreads, 4) tile_kernel(RenderParams P) {
     s_ray = lo;
     const unsigned *off = P.item_off + (size_t)lo * P.nl;
     const unsigned base = off[0], M = off[P.nl] - base;
-    const unsigned g0 = (blockIdx.x - P.cta_off[lo]) * kTileThreads;
-    const unsigned g1 = min(g0 + kTileThreads, M) - 1;
+    // the ray's items are split evenly over its tiles
+    const unsigned nt = P.cta_off[lo + 1] - P.cta_off[lo], k = blockIdx.x - P.cta_off[lo];
+    const unsigned per = (M + nt - 1) / nt;
+    const unsigned g0 = min(k * per, M), g1 = min(g0 + per, M);  // [g0, g1)
+    s_g0 = g0;
+    s_g1 = g1;
+    s_M = M;
     // lines of the first and last item: largest l with off[l]-base <= g
+    const unsigned gf = min(g0, M - 1), gl = min(max(g1, g0 + 1) - 1, M - 1);
     int a = 0, b = P.nl;
     while (b - a > 1) {
       const int mid = (a + b) >> 1;
-      if (off[mid] - base <= g0) a = mid;
+      if (off[mid] - base <= gf) a = mid;
       else b = mid;
     }
     s_l0 = a;
     b = P.nl;
     while (b - a > 1) {
       const int mid = (a + b) >> 1;
-      if (off[mid] - base <= g1) a = mid;
+      if (off[mid] - base <= gl) a = mid;
       else b = mid;
     }
     s_l1 = a;
   }
   __syncthreads();
   const int ray = s_ray, l0 = s_l0, nlc = s_l1 - s_l0 + 1;
-  const unsigned *off = P.item_off + (size_t)ray * P.nl;
-  const unsigned base = off[0], M = off[P.nl] - base;
-  const unsigned my = (blockIdx.x - P.cta_off[ray]) * kTileThreads + tid;
-  const bool active = my < M;
-  // my line and channel
-  int l = l0;
-  if (active) {
+  const unsigned g0 = s_g0, g1 = s_g1;
+  // my item: g0 + tid; surplus threads shadow the tile's first item and store nothing
+  Item it;
+  {
+    const unsigned *off = P.item_off + (size_t)ray * P.nl;
+    const unsigned base = off[0];
+    unsigned my = g0 + tid;
+    if (my >= g1) my = min(g0, s_M - 1);
     int a = l0, b = s_l1 + 1;
     while (b - a > 1) {
       const int mid = (a + b) >> 1;
       if (off[mid] - base <= my) a = mid;
       else b = mid;
     }
-    l = a;
+    const int4 rg = P.rng[(long long)ray * P.nl + a];
+    bool msk = false;
+    const int ch = task_chan(P, rg, (int)(my - (off[a] - base)), msk);
+    s_meta[tid] = make_int2(a, ch | (msk ? 0x40000000 : 0));
+    s_dnu[tid] = P.line_dnu[(size_t)a * P.nfr + ch];
+    s_flags[tid] = 0;
+    it.inten = (P.out_itype == 3) ? P.isrf_line[(size_t)a * P.nfr + ch] : P.lines[a].i_outer;
+    it.src0 = it.alp0 = it.r0 = 0.0;
   }
-  const int ml = l - l0;
-  const long long task = (long long)ray * P.nl + l;
-  const int4 rg = P.rng[task];
-  bool masked = false;
-  const int ch = active ? task_chan(P, rg, (int)(my - (off[l] - base)), masked) : 0;
-  const LineDev L = P.lines[l];
-  const double dnu = P.line_dnu[(size_t)l * P.nfr + ch];
-  double inten = (P.out_itype == 3) ? P.isrf_line[(size_t)l * P.nfr + ch] : L.i_outer;
   const long long n0 = P.node_off[ray];
   const int N = (int)(P.node_off[ray + 1] - n0);
-  // shared-memory carve-up: StagedNode[nch+1] then StagedLine[(nch+1)*nlc]
-  int nch = (P.smem_budget - (int)sizeof(StagedNode)) / (int)(nlc * sizeof(StagedLine) + sizeof(StagedNode)) - 1;
+  // shared-memory carve-up: two buffers of (nch+1) slots
+  int nch = (P.smem_budget / 2) / (nlc * kPairBytes + kSlotBytes) - 1;
   nch = max(1, min(kTileChunk, nch));
-  StagedNode *sn = reinterpret_cast<StagedNode *>(smem_raw);
-  StagedLine *sl = reinterpret_cast<StagedLine *>(sn + (nch + 1));
-  double src0 = 0.0, alp0 = 0.0, r0 = 0.0;
-  int init = 1, maser = 0;
-  unsigned nelem = 0;
-  for (int c0 = 1; c0 < N; c0 += nch) {
-    const int cnt = min(nch, N - c0);
-    // ---- stage nodes c0-1 .. c0+cnt-1 (slot 0 = the previous node) ----
-    for (int p = tid; p < (cnt + 1) * nlc; p += kTileThreads) {
-      const int slot = p / nlc, m = p - slot * nlc;
-      const int node = c0 - 1 + slot;
-      const Node nd = load_node(P.nodes.rec, n0 + node);
-      const LineDev Lm = P.lines[l0 + m];
-      const double4 v = gather_line(P.cellL + (size_t)(l0 + m) * P.ncell, nd.cells, nd.wr, nd.wt,
-                                    nd.flags & kFlagIcrMask);
-      const double lw_prev = (node > 0) ? __ldg(&P.nodes.rec[n0 + node - 1].lw) : nd.lw;
-      const double lwav = 0.5 * (lw_prev + nd.lw);
-      StagedLine s;
-      s.srcd = v.x;
-      s.alpd = v.y;
-      s.cN = Lm.c_src * v.z;
-      s.kk = Lm.c_alp * (v.w * Lm.bdu - v.z * Lm.bud);
-      s.inv_aa = 1.0 / (Lm.k_aa * lwav);
-      s.nudv = Lm.nu0 * nd.dvmu;
-      const double norm = 0.56419583546 * s.inv_aa;
-      s.A1 = s.cN * norm;
-      s.K1 = s.kk * norm;
-      sl[slot * nlc + m] = s;
-      if (m == 0) {
-        StagedNode t;
-        t.ds = nd.ds;
-        t.dvmu = nd.dvmu;
-        t.q = nd.q;
-        t.lwav = lwav;
-        t.flags = nd.flags;
-        t.pad0 = t.pad1 = t.pad2 = 0;
-        sn[slot] = t;
-      }
-    }
+  const int bufbytes = (nch + 1) * (nlc * kPairBytes + kSlotBytes);
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  auto make_buf = [&](int b) {
+    TileBuf t;
+    t.hn = smem0 + (uint32_t)(b * bufbytes);
+    t.cn = t.hn + (uint32_t)((nch + 1) * sizeof(HotNode));
+    t.hl = t.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
+    t.cl = t.hl + (uint32_t)((nch + 1) * nlc * sizeof(HotLine));
+    return t;
+  };
+  bool r0ok = false;
+  if (N > 1) {
+    stage_chunk<NT>(P, make_buf(0), nlc, l0, n0, 1, min(nch, N - 1), tid);
     __syncthreads();
-    if (active) {
-      for (int slot = 1; slot <= cnt; slot++) {
-        const StagedNode ns = sn[slot];
-        const StagedLine s1 = sl[slot * nlc + ml];
-        const double ds = ns.ds, hds = 0.5 * ns.ds;
-        if (ns.flags & (kFlagInit | kFlagStar | kFlagZero)) {  // inner hole / inner boundary (rare)
-          if (ns.flags & kFlagZero) inten = 0.0;
-          if (ns.flags & kFlagStar)
-            inten = (1.0 - P.starfract) * inten + P.starfract * P.star_line[(size_t)l * P.nfr + ch];
-          init = 1;
-        }
-        if (P.subgrid && (2.0 * 3.0 * ns.q > 1.0)) {  // line.F:4715 (rare)
-          const double dvmu0 = sn[slot - 1].dvmu;
-          const double s_c = ds * (dnu * L.inv_nu0 - dvmu0) / (ns.dvmu - dvmu0);
-          const double dls3 = 3.0 * (ds / ns.q);
-          const double sright = s_c + dls3, sleft = s_c - dls3;
-          if (sright > 0.0 && sleft < ds) {
-            const StagedLine s0 = sl[(slot - 1) * nlc + ml];
-            double srcl0 = src0 - s0.srcd, alpl0 = alp0 - s0.alpd;
-            nelem += subgrid_tile(L, dnu, inten, ds, sleft, sright, s0.srcd, s0.alpd, s0.cN, s0.kk, dvmu0,
-                                  s1.srcd, s1.alpd, s1.cN, s1.kk, ns.dvmu, ns.lwav, srcl0, alpl0, init);
-            src0 = s1.srcd + srcl0;
-            alp0 = s1.alpd + alpl0;
-            r0 = src0 * rcp_fast(alp0);
-            init = 0;
-            if (alpl0 * ds < (double)(-0.01f)) maser = 1;
-            continue;
-          }
-        }
-        if (init) {  // first segment of the ray / after the inner hole (rare): line.F:4559-4586
-          const StagedLine s0 = sl[(slot - 1) * nlc + ml];
-          const double u0 = (dnu - s0.nudv) * s1.inv_aa;
-          const double phi0 = 0.56419583546 * s1.inv_aa * exp_neg_tab(-(u0 * u0), s_exptab);
-          src0 = s0.srcd + s0.cN * phi0;
-          alp0 = s0.alpd + s0.kk * phi0;
-          r0 = src0 * rcp_fast(alp0);
-          init = 0;
-        }
-        // line.F:4554-4597 + transfer.F:1498-1571, straight line
-        const double u1 = (dnu - s1.nudv) * s1.inv_aa;
-        const double e1g = exp_neg_tab(-(u1 * u1), s_exptab);
-        const double alpl1 = s1.K1 * e1g;
-        const double src1 = fma(s1.A1, e1g, s1.srcd);
-        const double alp1 = s1.alpd + alpl1;
-        const double dtau = hds * (alp0 + alp1);
-        const double theomax = hds * (src0 + src1);
-        const double r1 = src1 * rcp_fast(alp1);
-        const double xpe = exp_neg_tab(-fabs(dtau), s_exptab);
-        const bool p0 = alp0 > 0.0, p1 = alp1 > 0.0;
-        const double s_a = p0 ? r0 : (p1 ? r1 : 0.0);
-        const double s_b = p1 ? r1 : (p0 ? r0 : 0.0);
-        const bool thick = dtau > 1.e-6;
-        const double e0 = 1.0 - xpe;
-        const double ee1 = dtau - e0;
-        const double bt = ee1 * rcp_fast(dtau);
-        const double hb = 0.5 * dtau;
-        const double b = thick ? bt : hb;
-        const double a = thick ? (e0 - bt) : hb;
-        const double x = thick ? xpe : (1.0 - dtau);
-        double qv = (dtau > (double)1e-9f) ? fma(a, s_a, b * s_b) : theomax;
-        qv = fmin(qv, theomax);
-        inten = fma(inten, x, qv);
-        src0 = src1;
-        alp0 = alp1;
-        r0 = r1;
-        if (s1.K1 < 0.0 && alpl1 * ds < (double)(-0.01f)) maser = 1;  // telescope.F:4295
-        nelem++;
-      }
+    int cur = 0;
+    for (int c0 = 1; c0 < N; c0 += nch, cur ^= 1) {
+      const int cnt = min(nch, N - c0);
+      const int c1 = c0 + nch;
+      if (c1 < N) stage_chunk<NT>(P, make_buf(cur ^ 1), nlc, l0, n0, c1, min(nch, N - c1), tid);
+      const TileBuf Bc = make_buf(cur);
+      integrate_chunk(P, Bc, nlc, cnt, it, l0, r0ok);
+      __syncthreads();
     }
-    __syncthreads();
   }
-  if (active) {
-    const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
-    P.img[row * P.nfr + ch] = inten;
-    if (P.integ) P.integ[row * P.nfr + ch] = masked ? 1 : 2;
-    if (maser) atomicOr(&P.maser[l], 1);
+  unsigned long long r = 0, x = 0;
+  if (g0 + tid < g1) {
+    const int2 mt = s_meta[tid];
+    const int ch = mt.y & 0x3fffffff;
+    const size_t row = (size_t)mt.x * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
+    P.img[row * P.nfr + ch] = it.inten;
+    if (P.sparse && it.inten == 0.0) P.dense[(long long)ray * P.nl + mt.x] = 2;  // see fill_sparse_kernel
+    if (P.integ) P.integ[row * P.nfr + ch] = (mt.y & 0x40000000) ? 1 : 2;
+    const unsigned f = s_flags[tid];
+    if (f & 1u) atomicOr(&P.maser[mt.x], 1);
+    r = 1;
+    x = f >> 8;
   }
-  // work counters
-  unsigned long long e = nelem, s = active ? (unsigned long long)(N > 0 ? N - 1 : 0) : 0, r = active ? 1 : 0;
+  // work counters: every item walks the ray's N-1 segments; sub-gridding adds extra elements
+  unsigned long long s = r * (unsigned long long)(N > 0 ? N - 1 : 0), e = s + x;
   for (int o = 16; o; o >>= 1) {
     e += __shfl_xor_sync(0xffffffffu, e, o);
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -707,60 +1020,86 @@ __global__ void plan_kernel(RenderParams P) {
   unsigned n = 0;
   if (ray < P.nray) {
     const unsigned M = P.item_off[(size_t)(ray + 1) * P.nl] - P.item_off[(size_t)ray * P.nl];
-    n = (M + kTileThreads - 1) / kTileThreads;
+    const unsigned T = (unsigned)(P.tile_threads * kTileIpt);
+    n = (M + T - 1) / T;
   }
   P.ncta[ray] = n;
 }
 
+// the rare case of telescope.F:583: the row's continuum is exactly zero, so the reference integrates
+// every skipped channel until one is non-zero.  Sequential; returns the counters of the extra work.
+__device__ __noinline__ void fill_zero_continuum(const RenderParams &P, long long task, int l, int ray,
+                                                 const int4 rg, double *I, double cont) {
+  unsigned long long e = 0, r = 0, s = 0;
+  for (int c = 1; c < P.nfr; c++) {
+    const bool in = (c >= rg.x && c <= rg.y);
+    if (in) continue;
+    if (cont != 0.0) {
+      I[c] = cont;
+    } else {
+      if (c != rg.z) {
+        double tau;
+        unsigned ne;
+        int maser = 0;
+        I[c] = integrate_ray_channel(P, l, ray, c, tau, ne, maser);
+        if (maser) atomicOr(&P.maser[l], 1);
+        e += ne;
+        r += 1;
+        s += (unsigned)(P.node_off[ray + 1] - P.node_off[ray] - 1);
+      }
+      cont = I[c];
+    }
+  }
+  if (r) {
+    atomicAdd(&P.counters[0], r);
+    atomicAdd(&P.counters[1], e);
+    atomicAdd(&P.counters[2], s);
+  }
+}
+
 // continuum copy for the channels the reference skips (telescope.F:557-612); one warp per task
-__global__ void __launch_bounds__(256) fill_kernel(RenderParams P) {
+// (cube / mask mode: every channel of the image is materialised)
+__global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ RenderParams P) {
   const int lane = threadIdx.x & 31;
   const long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long ntask = (long long)P.nl * P.nray;
   if (task >= ntask) return;
   const int ray = (int)(task / P.nl), l = (int)(task % P.nl);
-  if (ray == 0 || !P.nonredundant) return;
+  if (ray == 0) return;
   const int4 rg = P.rng[task];
   const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
   double *I = P.img + row * P.nfr;
   // continuum known after channel 0 (if out of range) or after the pre-integrated channel c0
-  double cont = (rg.w == 0) ? I[0] : (rg.z >= 0 ? I[rg.z] : 0.0);
+  const double cont = (rg.w == 0) ? I[0] : (rg.z >= 0 ? I[rg.z] : 0.0);
   if (cont != 0.0) {
     for (int c = 1 + lane; c < P.nfr; c += 32) {
       const bool in = (c >= rg.x && c <= rg.y);
       if (!in && c != rg.z) I[c] = cont;
     }
+  } else if (lane == 0) {
+    fill_zero_continuum(P, task, l, ray, rg, I, cont);
+  }
+}
+
+// spectrum mode (no cube, no mask requested): the continuum copies are not materialised -- the ring
+// sum synthesises the skipped channels from the row's continuum channel.  Only rows on which
+// tile_kernel saw an exactly zero intensity (dense[task] == 2) are examined here; if their continuum
+// is zero they are completed like in cube mode and stay flagged dense (1) for the ring sum.
+__global__ void __launch_bounds__(256) fill_sparse_kernel(const __grid_constant__ RenderParams P) {
+  const long long task = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ntask = (long long)P.nl * P.nray;
+  if (task >= ntask || P.dense[task] == 0) return;
+  const int ray = (int)(task / P.nl), l = (int)(task % P.nl);
+  const int4 rg = P.rng[task];
+  const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
+  double *I = P.img + row * P.nfr;
+  const double cont = (rg.w == 0) ? I[0] : (rg.z >= 0 ? I[rg.z] : 0.0);
+  if (cont != 0.0) {
+    P.dense[task] = 0;
     return;
   }
-  // rare: the continuum is exactly zero, so the reference integrates every skipped channel until
-  // one is non-zero (imcir_cont.ne.0 test, telescope.F:583).  Sequential, lane 0.
-  if (lane == 0) {
-    unsigned long long e = 0, r = 0, s = 0;
-    for (int c = 1; c < P.nfr; c++) {
-      const bool in = (c >= rg.x && c <= rg.y);
-      if (in) continue;
-      if (cont != 0.0) {
-        I[c] = cont;
-      } else {
-        if (c != rg.z) {
-          double tau;
-          unsigned ne;
-          int maser = 0;
-          I[c] = integrate_ray_channel(P, l, ray, c, tau, ne, maser);
-          if (maser) atomicOr(&P.maser[l], 1);
-          e += ne;
-          r += 1;
-          s += (unsigned)(P.node_off[ray + 1] - P.node_off[ray] - 1);
-        }
-        cont = I[c];
-      }
-    }
-    if (r) {
-      atomicAdd(&P.counters[0], r);
-      atomicAdd(&P.counters[1], e);
-      atomicAdd(&P.counters[2], s);
-    }
-  }
+  fill_zero_continuum(P, task, l, ray, rg, I, cont);
+  P.dense[task] = 1;
 }
 
 // replicate the centre ray over phi (telescope.F:524-526) -- only when the cube is requested
@@ -786,7 +1125,19 @@ __global__ void __launch_bounds__(128) ringsum_kernel(RenderParams P, const doub
   const int l = (int)(i / ((long long)P.nfr * P.nrr));
   const double *I = P.img + ((size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)ir * P.nphi) * P.nfr + c;
   double dslum = 0.0;
-  for (int ip = 0; ip < P.nphi; ip++) dslum = dslum + I[(size_t)ip * P.nfr];
+  if (!P.sparse || !P.nonredundant) {
+    for (int ip = 0; ip < P.nphi; ip++) dslum = dslum + I[(size_t)ip * P.nfr];
+  } else {
+    // skipped channels carry the row's continuum (telescope.F:582-612), never written in this mode
+    long long task = ((long long)(1 + (ir - 1) * P.nphi)) * P.nl + l;
+    for (int ip = 0; ip < P.nphi; ip++, task += P.nl) {
+      const int4 rg = __ldg(&P.rng[task]);
+      const double *row = I - c + (size_t)ip * P.nfr;
+      const bool own = (c == 0) || (c >= rg.x && c <= rg.y) || (c == rg.z) || P.dense[task];
+      const int src = own ? c : ((rg.w == 0) ? 0 : rg.z);
+      dslum = dslum + row[src];
+    }
+  }
   dslum = dslum / (1.0 * P.nphi);
   dslum = dslum * surf[ir];
   ring[i] = dslum;
@@ -844,31 +1195,43 @@ void launch_prep(const PrepParams &P, cudaStream_t st) {
   prep_cells_kernel<<<grid, 256, 0, st>>>(P);
 }
 void launch_span(const RenderParams &P, cudaStream_t st) {
-  const long long ntask = (long long)P.nl * P.nray;
-  const long long threads = ntask * 32;
-  span_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P);
+  if (P.nonredundant) mask_kernel<<<(unsigned)((P.ncell * 4 + 255) / 256), 256, 0, st>>>(P);
+  span_kernel<<<(unsigned)P.nray, kSpanThreads, 0, st>>>(P);
 }
 void launch_plan(const RenderParams &P, cudaStream_t st) {
   plan_kernel<<<(P.nray + 1 + 255) / 256, 256, 0, st>>>(P);
 }
-int tile_smem_limit() {
+// dynamic shared memory per tile_kernel block: 20 warps per SM stay resident next to the 14 KB of
+// exp tables and item metadata each block carries (5 x 128 or 10 x 64 threads)
+int tile_smem_limit(int threads) {
   static int done = 0;
-  const int want = 44 * 1024;  // 4 blocks/SM of 128 threads stay resident
+  const int want128 = 29 * 1024, want64 = 7 * 1024;
   if (!done) {
-    cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    cudaFuncSetAttribute(tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, want128);
+    cudaFuncSetAttribute(tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, want64);
     done = 1;
   }
-  return want;
+  return threads == 128 ? want128 : want64;
+}
+// most lines a tile may span so that two buffers of two slots fit the budget
+int tile_max_lines(int threads) {
+  return (tile_smem_limit(threads) / 4 - kSlotBytes) / kPairBytes;
 }
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
   center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);
   if (!total_ctas) return;
-  tile_kernel<<<total_ctas, kTileThreads, P.smem_budget, st>>>(P);
+  if (P.tile_threads == 128) tile_kernel<128><<<total_ctas, 128, P.smem_budget, st>>>(P);
+  else tile_kernel<64><<<total_ctas, 64, P.smem_budget, st>>>(P);
 }
 void launch_fill(const RenderParams &P, cudaStream_t st) {
+  if (!P.nonredundant) return;  // every channel was integrated
   const long long ntask = (long long)P.nl * P.nray;
-  const long long threads = ntask * 32;
-  fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P);
+  if (P.sparse) {
+    fill_sparse_kernel<<<(unsigned)((ntask + 255) / 256), 256, 0, st>>>(P);
+  } else {
+    const long long threads = ntask * 32;
+    fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P);
+  }
 }
 void launch_center_replicate(const RenderParams &P, cudaStream_t st) {
   const long long n = (long long)P.nl * (P.nphi - 1) * P.nfr;

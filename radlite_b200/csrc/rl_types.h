@@ -13,14 +13,16 @@ constexpr int kRayAdpt = 4;
 constexpr int kRayRnpt = 4;
 constexpr int kMaxExtra = 40;  // 2 + 4*RAYADPT*2 = 34 used
 constexpr int kLgNrMax = 31;   // line.F:4657-4661
-constexpr int kTileThreads = 128;  // threads (= ray-channel items) per tile_kernel block
-constexpr int kTileChunk = 32;     // nodes staged in shared memory per pass
+constexpr int kTileIpt = 1;        // ray-channel items per tile_kernel thread
+constexpr int kTileChunk = 32;     // nodes staged in shared memory per pass (upper bound)
+constexpr int kSpanThreads = 128;  // span_kernel block = lines per batch upper bound (one mask bit per line)
 
 // node flags (low 2 bits = tr_icross: 1 = R crossing, 2 = theta crossing, 3 = extra point)
 constexpr uint32_t kFlagIcrMask = 3u;
 constexpr uint32_t kFlagInit = 4u;   // carried profile state is reset before this segment
 constexpr uint32_t kFlagStar = 8u;   // centre beam: mix in the star before this segment
 constexpr uint32_t kFlagZero = 16u;  // inner BC type 1: intensity := 0 before this segment
+constexpr uint32_t kFlagSub = 32u;   // 6 q > 1: the segment ending here may be velocity sub-gridded (line.F:4715)
 
 // ghosted grids: rc[i+1] = rsi_x_c(i,1), i=-1..nr+2 ; tc[i+1] = rsi_x_c(i,2), i=-1..nt+2 ;
 // ridx[i+4] = ridx_it(i), i=-4..nt+4
@@ -38,16 +40,16 @@ struct GridDev {
 // Node lists of all rays: one 64-byte record per node, ray r owns [node_off[r], node_off[r+1]).
 // The record is read as four 16-byte loads; all lanes working on the same ray read the same
 // address (broadcast), so an array of structures is the right layout here.
-constexpr int kCellFlagShift = 27;                 // cells.x = cell(t0,r0) | flags << 27
+constexpr int kCellFlagShift = 26;                 // cells.x = cell(t0,r0) | flags << 26
 constexpr int kCellMask = (1 << kCellFlagShift) - 1;
 struct __align__(16) NodeRec {
   double ds;    // segment length to the previous node (vacuum rule applied); 0 for a ray's first node
   double dvmu;  // Omega.v/c at the node (line independent)
   double lw;    // interpolated line width [km/s]
-  double q;     // |dvmu - dvmu_prev| / (0.5 (lw+lw_prev)/c): the sub-grid trigger of line.F:4706-4709
+  double inv_lwav;  // 1 / (0.5 (lw + lw_prev)): reciprocal mean width of the segment ending here (1/lw for node 0)
   double wr;    // dr
   double wt;    // dt
-  int4 cells;   // cells (t0,r0)|flags<<27, (t1,r0), (t0,r1), (t1,r1)
+  int4 cells;   // cells (t0,r0)|flags<<26, (t1,r0), (t0,r1), (t1,r1)
 };
 struct NodesDev {
   NodeRec *rec;
@@ -80,6 +82,12 @@ struct LineDev {
   // derived constants (host): line.F:2301 aa = k_aa * width ; line.F:4571-4588 j_l = c_src N_up phi,
   // alpha_l = c_alp (N_down B_du - N_up B_ud) phi
   double k_aa, c_src, c_alp, inv_nu0;
+  double kia;  // sqrt(2^18/ln 2) / k_aa: scaled reciprocal Doppler width per unit 1/width (tile_kernel)
+};
+
+// per cell, one bit per line of the batch: N_up + N_down surely above / surely below LEVTHRES
+struct __align__(16) CellMask {
+  uint4 on, off;
 };
 
 struct RenderParams {
@@ -109,6 +117,10 @@ struct RenderParams {
   unsigned int *ncta;        // [nray+1] thread blocks of tile_kernel per ray
   const unsigned int *cta_off;   // [nray+1] exclusive scan of ncta
   int smem_budget;           // dynamic shared memory per tile_kernel block [bytes]
+  int tile_threads;          // threads per tile_kernel block (64 or 128); a tile = tile_threads * kTileIpt items
+  CellMask *masks;           // [ncell]
+  int sparse;                // 1: skipped channels are not materialised in img (spectrum only)
+  unsigned char *dense;      // [ntask] sparse mode: row was completed by fill_kernel
   double *img;               // [nl][nrr+1][nphi][nfr]
   unsigned char *integ;      // [nl][nrow][nfr] 1 = channel was integrated with cmask=1
   double *tau_center;        // [nl]

@@ -153,6 +153,19 @@ def test_repeatable_bitwise_and_mask_accumulates(renderer_cls):
     assert np.all(a["cmask"][1] >= a["cmask"][0]) and np.all(a["cmask"][2] >= a["cmask"][1])
 
 
+def test_spectrum_only_equals_cube_mode(renderer_cls):
+    """Spectrum-only renders never materialise the continuum copies of the skipped channels (the ring
+    sum synthesises them); the flux must be bit-identical to the cube-mode render, including rows
+    whose continuum is exactly zero (completed by the fallback) and NONREDUNDANT off."""
+    for m in (tiny(2, nlines=3), static_uniform_shell(rho=1e-20, abund=1e-8), clone(tiny(2, nlines=2), nonredundant=0)):
+        g = renderer_cls(0)
+        g.load_model(m)
+        a = g.render(1, m.nlines, m.nfr, m.passband, synth.PARSEC, want_image=True, want_mask=True)
+        b = g.render(1, m.nlines, m.nfr, m.passband, synth.PARSEC)
+        assert np.array_equal(a["flux"], b["flux"])
+        assert np.array_equal(a["maserflag"], b["maserflag"])
+
+
 def test_error_codes_match_reference_stops(renderer_cls):
     m = tiny()
     g = renderer_cls(0)
