@@ -22,7 +22,7 @@ void launch_geom(const GeomParams &P, bool count, cudaStream_t st);
 void launch_prep(const PrepParams &P, cudaStream_t st);
 void launch_span(const RenderParams &P, cudaStream_t st);
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st);
-void launch_plan(const RenderParams &P, cudaStream_t st);
+void launch_plan(const RenderParams &P, bool fill, cudaStream_t st);
 int tile_smem_limit(int threads);
 int tile_max_lines(int threads);
 void launch_fill(const RenderParams &P, cudaStream_t st);
@@ -128,6 +128,7 @@ struct rl_ctx {
   DevBuf<double> d_wgt, d_freq, d_ld_src, d_ld_alp;
   DevBuf<int4> d_rng;
   DevBuf<CellMask> d_masks;
+  DevBuf<TileDesc> d_tiles;
   DevBuf<unsigned char> d_dense;
   DevBuf<unsigned int> d_nitems, d_item_off, d_ncta, d_cta_off;
   DevBuf<unsigned char> d_scan_tmp;
@@ -641,7 +642,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
   // tile_kernel: 128-thread blocks when a ray carries enough (line, channel) items, else 64; a tile
   // must hold two slots of all its lines in shared memory twice (double buffer)
   const int tile_threads = (lb >= 16) ? 128 : 64;
-  lb = std::min(lb, tile_max_lines(tile_threads));
+  // (the lines a tile spans are bounded by plan_kernel, not by the batch size)
   lb = std::min(lb, kSpanThreads);  // span_kernel: one thread and one mask bit per line
   if (want_mask) {
     const long long per = (long long)nrow * nfr;
@@ -829,6 +830,8 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.cta_off = c->d_cta_off.p;
     P.tile_threads = tile_threads;
     P.smem_budget = tile_smem_limit(tile_threads);
+    P.tile_max_lines = tile_max_lines(tile_threads);
+    P.tiles = nullptr;
     P.img = c->d_img.p;
     P.integ = want_mask ? c->d_integ.p : nullptr;
     P.tau_center = c->d_tau.p;
@@ -845,7 +848,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
                                        (int)(ntask + 1), c->st));
       c->launches++;
     }
-    launch_plan(P, c->st);
+    launch_plan(P, false, c->st);
     c->launches++;
     {
       size_t tmp_bytes = 0;
@@ -859,6 +862,12 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     CU(cudaMemcpyAsync(&total_ctas, c->d_cta_off.p + c->nray, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
     CU(cudaEventRecord(c->ev[2], c->st));
     CU(cudaStreamSynchronize(c->st));
+    CU(c->d_tiles.ensure(std::max<size_t>(1, total_ctas)));
+    P.tiles = c->d_tiles.p;
+    if (total_ctas) {
+      launch_plan(P, true, c->st);
+      c->launches++;
+    }
     // ---- ray integration ----
     launch_integrate(P, total_ctas, c->st);
     CU(cudaEventRecord(c->ev[5], c->st));

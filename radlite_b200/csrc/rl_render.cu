@@ -739,91 +739,71 @@ __device__ __noinline__ void stage_chunk(const RenderParams &P, const TileBuf &B
   }
 }
 
-// raw staged data of one slot for one item, and what the profile evaluation makes of it
-struct RawSlot {
-  double2 sa, ak, iv;  // HotLine
-  double hds;
-  uint32_t fl;
-};
+// what the profile evaluation makes of one staged slot for one item (line.F:4554-4597 at the end
+// point of the segment: profile, line + dust source and opacity)
 struct PreSlot {
   double src1, alp1, alpl1, hds;
   uint32_t fl;
-  bool k1neg;
+  int k1hi;  // high word of K1: its sign flags inverted populations
 };
-__device__ __forceinline__ RawSlot raw_load(uint32_t an, uint32_t ah) {
-  RawSlot r;
-  unsigned long long fw;
-  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(r.hds), "=l"(fw) : "r"(an));
-  r.fl = (uint32_t)fw;
-  r.iv = lds_f64x2(ah + 32);
-  r.ak = lds_f64x2(ah + 16);
-  r.sa = lds_f64x2(ah);
-  return r;
-}
-// line.F:4554-4597 at the end point of the segment: profile, line + dust source and opacity
-__device__ __forceinline__ PreSlot pre_compute(const RawSlot &r, double dnu, uint32_t T1, uint32_t T2) {
+__device__ __forceinline__ PreSlot pre_slot(uint32_t an, uint32_t ah, double dnu, uint32_t T1, uint32_t T2) {
   PreSlot g;
-  const double u = fma(dnu, r.iv.x, -r.iv.y);
+  unsigned long long fw;
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(g.hds), "=l"(fw) : "r"(an));
+  g.fl = (uint32_t)fw;
+  const double2 iv = lds_f64x2(ah + 32), ak = lds_f64x2(ah + 16), sa = lds_f64x2(ah);
+  const double u = fma(dnu, iv.x, -iv.y);
   const double e = gauss_tab(u, T1, T2);
-  g.alpl1 = r.ak.y * e;
-  g.src1 = fma(r.ak.x, e, r.sa.x);
-  g.alp1 = r.sa.y + g.alpl1;
-  g.hds = r.hds;
-  g.fl = r.fl;
-  g.k1neg = __double2hiint(r.ak.y) < 0;
+  g.alpl1 = ak.y * e;
+  g.src1 = fma(ak.x, e, sa.x);
+  g.alp1 = sa.y + g.alpl1;
+  g.k1hi = __double2hiint(ak.y);
   return g;
 }
 
-// the segments of one staged chunk for the thread's item, software pipelined two slots deep: while
-// the carried intensity is advanced over slot s, the profile of slot s+1 is evaluated (it does not
-// depend on the carried state) and the staged record of slot s+2 is in flight from shared memory.
-// Flagged nodes (rare) are handled by an out-of-line call between runs of the register-resident
-// loop; everything but the item state is re-materialised after such a call (manual live-range
-// splitting: nothing else is live across it).
+// the segments of one staged chunk for the thread's item, software pipelined: the profile of slot
+// s+1 (which does not depend on the carried state) is evaluated in the same basic block as the
+// optical-depth test of slot s, so its shared-memory and table latencies overlap.  The slot after
+// the chunk's last one is a phantom (stale data, read but never used).  Flagged nodes (rare) are
+// handled by an out-of-line call between runs of the register-resident loop; everything but the
+// item state is re-materialised after such a call (manual live-range splitting).
 __device__ __forceinline__ void integrate_chunk(const RenderParams &P, const TileBuf B, int nlc, int cnt,
-                                                Item &it, int l0, bool &r0ok) {
+                                                Item &it, int l0, int &r0ok) {
   const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1), T2 = (uint32_t)__cvta_generic_to_shared(s_T2);
   int slot = 1;
   while (slot <= cnt) {
     const uint32_t stride = (uint32_t)nlc * (uint32_t)sizeof(HotLine);
     const double dnu = s_dnu[threadIdx.x];
-    const uint32_t aoff = (uint32_t)(s_meta[threadIdx.x].x - l0) * (uint32_t)sizeof(HotLine);
-    // slot indices beyond cnt are clamped to cnt: their values are never used
-    const int s1 = min(slot + 1, cnt);
-    PreSlot cur = pre_compute(raw_load(B.hn + (uint32_t)slot * (uint32_t)sizeof(HotNode),
-                                       B.hl + (uint32_t)slot * stride + aoff), dnu, T1, T2);
-    uint32_t an = B.hn + (uint32_t)s1 * (uint32_t)sizeof(HotNode), ah = B.hl + (uint32_t)s1 * stride + aoff;
-    RawSlot rawA = raw_load(an, ah), rawB;
-    PreSlot curB;
-    // one pipeline beat: fetch slot+2 into `rout`, evaluate the profile of slot+1 from `rin` into
-    // `pout`, advance the intensity over `slot` with `pin`.  Unrolled twice with the roles of the A
-    // and B registers swapped, so that nothing has to be moved between beats.
-#define RL_BEAT(pin, rin, pout, rout)                                                              \
+    uint32_t an = B.hn + (uint32_t)slot * (uint32_t)sizeof(HotNode);
+    uint32_t ah = B.hl + (uint32_t)slot * stride +
+                  (uint32_t)(s_meta[threadIdx.x].x - l0) * (uint32_t)sizeof(HotLine);
+    PreSlot pa = pre_slot(an, ah, dnu, T1, T2), pb;
+    // one pipeline beat: evaluate the profile of slot+1 into `pout`, advance the intensity over
+    // `slot` with `pin`.  Unrolled twice with the roles of the A and B registers swapped.
+#define RL_BEAT(pin, pout)                                                                         \
   {                                                                                                \
-    const bool more = slot + 2 <= cnt;                                                             \
-    an += more ? (uint32_t)sizeof(HotNode) : 0u;                                                   \
-    ah += more ? stride : 0u;                                                                      \
-    rout = raw_load(an, ah);                                                                       \
-    pout = pre_compute(rin, dnu, T1, T2);                                                          \
-    if (pin.fl) break; /* block-uniform: this node takes the out-of-line path */                   \
-    /* advance the intensity over slot (transfer.F:1498-1571) */                                   \
+    an += (uint32_t)sizeof(HotNode);                                                               \
+    ah += stride;                                                                                  \
+    /* transfer.F:1498-1571 for `slot` */                                                          \
     const double dtau = pin.hds * (it.alp0 + pin.alp1);                                            \
     const double theo = pin.hds * (it.src0 + pin.src1);                                            \
     /* inverted populations (K1 < 0) force the full path, which carries the maser test */          \
-    const bool work = (dtau > (double)1e-9f) | pin.k1neg;                                          \
+    const bool work = (dtau > (double)1e-9f) || (pin.k1hi < 0);                                    \
+    pout = pre_slot(an, ah, dnu, T1, T2);                                                          \
+    if (pin.fl) break; /* block-uniform: this node takes the out-of-line path */                   \
     if (!__any_sync(0xffffffffu, work)) {                                                          \
       /* transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau */                                  \
       it.inten = fma(it.inten, 1.0 - dtau, theo);                                                  \
-      r0ok = false;                                                                                \
+      r0ok = 0;                                                                                    \
     } else {                                                                                       \
       if (!r0ok) it.r0 = div_fast(it.src0, it.alp0);                                               \
       double r1;                                                                                   \
       full_step(it.inten, it.alp0, it.r0, pin.src1, pin.alp1, r1, dtau, theo, T1, T2);             \
       it.r0 = r1;                                                                                  \
-      if (__any_sync(0xffffffffu, pin.k1neg)) { /* telescope.F:4295 */                             \
+      if (__any_sync(0xffffffffu, pin.k1hi < 0)) { /* telescope.F:4295 */                          \
         if (pin.alpl1 * (pin.hds + pin.hds) < (double)(-0.01f)) s_flags[threadIdx.x] |= 1u;        \
       }                                                                                            \
-      r0ok = true;                                                                                 \
+      r0ok = 1;                                                                                    \
     }                                                                                              \
     it.src0 = pin.src1;                                                                            \
     it.alp0 = pin.alp1;                                                                            \
@@ -831,8 +811,8 @@ __device__ __forceinline__ void integrate_chunk(const RenderParams &P, const Til
     if (slot > cnt) break;                                                                         \
   }
     for (;;) {
-      RL_BEAT(cur, rawA, curB, rawB)
-      RL_BEAT(curB, rawB, cur, rawA)
+      RL_BEAT(pa, pb)
+      RL_BEAT(pb, pa)
     }
 #undef RL_BEAT
     if (slot > cnt) break;
@@ -846,7 +826,7 @@ __device__ __forceinline__ void integrate_chunk(const RenderParams &P, const Til
       it.alp0 = st[2];
       it.r0 = st[3];
       if (f) s_flags[threadIdx.x] = (s_flags[threadIdx.x] | (f & 1u)) + ((f >> 1) << 8);
-      r0ok = true;
+      r0ok = 1;
       slot++;
     }
   }
@@ -855,60 +835,23 @@ __device__ __forceinline__ void integrate_chunk(const RenderParams &P, const Til
 template <int NT>
 __global__ void __launch_bounds__(NT, 640 / NT) tile_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ double4 smem_raw[];
-  __shared__ int s_ray, s_l0, s_l1;
-  __shared__ unsigned s_g0, s_g1, s_M;
   const int tid = threadIdx.x, lane = tid & 31;
   for (int j = tid; j < 512; j += NT) {
     s_T1[j] = exp2((double)j * (1.0 / 512.0));
     const double w = exp2((double)j * (1.0 / 262144.0));
     s_T2[j] = make_double2(w, w * kLn2S);
   }
-  if (tid == 0) {
-    // which ray does this block belong to: largest r with cta_off[r] <= blockIdx.x
-    int lo = 0, hi = P.nray;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (P.cta_off[mid] <= blockIdx.x) lo = mid;
-      else hi = mid;
-    }
-    s_ray = lo;
-    const unsigned *off = P.item_off + (size_t)lo * P.nl;
-    const unsigned base = off[0], M = off[P.nl] - base;
-    // the ray's items are split evenly over its tiles
-    const unsigned nt = P.cta_off[lo + 1] - P.cta_off[lo], k = blockIdx.x - P.cta_off[lo];
-    const unsigned per = (M + nt - 1) / nt;
-    const unsigned g0 = min(k * per, M), g1 = min(g0 + per, M);  // [g0, g1)
-    s_g0 = g0;
-    s_g1 = g1;
-    s_M = M;
-    // lines of the first and last item: largest l with off[l]-base <= g
-    const unsigned gf = min(g0, M - 1), gl = min(max(g1, g0 + 1) - 1, M - 1);
-    int a = 0, b = P.nl;
-    while (b - a > 1) {
-      const int mid = (a + b) >> 1;
-      if (off[mid] - base <= gf) a = mid;
-      else b = mid;
-    }
-    s_l0 = a;
-    b = P.nl;
-    while (b - a > 1) {
-      const int mid = (a + b) >> 1;
-      if (off[mid] - base <= gl) a = mid;
-      else b = mid;
-    }
-    s_l1 = a;
-  }
-  __syncthreads();
-  const int ray = s_ray, l0 = s_l0, nlc = s_l1 - s_l0 + 1;
-  const unsigned g0 = s_g0, g1 = s_g1;
+  const TileDesc td = P.tiles[blockIdx.x];
+  const int ray = td.ray, l0 = td.l0, nlc = td.nlc;
+  const unsigned g0 = td.g0, g1 = td.g1;
   // my item: g0 + tid; surplus threads shadow the tile's first item and store nothing
   Item it;
   {
     const unsigned *off = P.item_off + (size_t)ray * P.nl;
     const unsigned base = off[0];
     unsigned my = g0 + tid;
-    if (my >= g1) my = min(g0, s_M - 1);
-    int a = l0, b = s_l1 + 1;
+    if (my >= g1) my = g0;
+    int a = l0, b = l0 + nlc;
     while (b - a > 1) {
       const int mid = (a + b) >> 1;
       if (off[mid] - base <= my) a = mid;
@@ -925,20 +868,23 @@ __global__ void __launch_bounds__(NT, 640 / NT) tile_kernel(const __grid_constan
   }
   const long long n0 = P.node_off[ray];
   const int N = (int)(P.node_off[ray + 1] - n0);
-  // shared-memory carve-up: two buffers of (nch+1) slots
-  int nch = (P.smem_budget / 2) / (nlc * kPairBytes + kSlotBytes) - 1;
+  // shared-memory carve-up: two buffers of nch+1 slots (+1 phantom slot of hn and hl, see
+  // integrate_chunk)
+  const int slot_bytes = nlc * kPairBytes + kSlotBytes, ph_bytes = nlc * (int)sizeof(HotLine) + (int)sizeof(HotNode);
+  int nch = (P.smem_budget / 2 - ph_bytes) / slot_bytes - 1;
   nch = max(1, min(kTileChunk, nch));
-  const int bufbytes = (nch + 1) * (nlc * kPairBytes + kSlotBytes);
+  const int bufbytes = (nch + 1) * slot_bytes + ph_bytes;
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   auto make_buf = [&](int b) {
     TileBuf t;
     t.hn = smem0 + (uint32_t)(b * bufbytes);
-    t.cn = t.hn + (uint32_t)((nch + 1) * sizeof(HotNode));
-    t.hl = t.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
-    t.cl = t.hl + (uint32_t)((nch + 1) * nlc * sizeof(HotLine));
+    t.hl = t.hn + (uint32_t)((nch + 2) * sizeof(HotNode));
+    t.cn = t.hl + (uint32_t)((nch + 2) * nlc * sizeof(HotLine));
+    t.cl = t.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
     return t;
   };
-  bool r0ok = false;
+  int r0ok = 0;
+  __syncthreads();  // exp tables
   if (N > 1) {
     stage_chunk<NT>(P, make_buf(0), nlc, l0, n0, 1, min(nch, N - 1), tid);
     __syncthreads();
@@ -1013,17 +959,56 @@ __global__ void __launch_bounds__(128) center_kernel(RenderParams P) {
   }
 }
 
-// thread blocks of tile_kernel per ray
+// tiles of a ray: its item list (lines in index order) is cut greedily into runs of at most
+// tile_threads items spanning at most tile_max_lines lines; the item budget is evened out over the
+// ray first.  FILL = false counts the tiles of every ray, FILL = true (after the scan) writes them.
+template <bool FILL>
 __global__ void plan_kernel(RenderParams P) {
   const int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray > P.nray) return;
   unsigned n = 0;
   if (ray < P.nray) {
-    const unsigned M = P.item_off[(size_t)(ray + 1) * P.nl] - P.item_off[(size_t)ray * P.nl];
-    const unsigned T = (unsigned)(P.tile_threads * kTileIpt);
-    n = (M + T - 1) / T;
+    const unsigned *off = P.item_off + (size_t)ray * P.nl;
+    const unsigned base = off[0], M = off[P.nl] - base;
+    if (M) {
+      const unsigned T0 = (unsigned)P.tile_threads;
+      const unsigned T = (M + (M + T0 - 1) / T0 - 1) / ((M + T0 - 1) / T0);  // ceil(M / ceil(M / T0))
+      const unsigned Lmax = (unsigned)P.tile_max_lines;
+      unsigned items = 0, lines = 0, g0 = 0;
+      int l0 = 0;
+      TileDesc *out = FILL ? P.tiles + P.cta_off[ray] : nullptr;
+      for (int l = 0; l < P.nl; l++) {
+        unsigned left = off[l + 1] - off[l];
+        while (left) {
+          if (items == T || lines == Lmax) {
+            if (FILL) {
+              TileDesc d;
+              d.ray = ray; d.g0 = g0; d.g1 = g0 + items; d.l0 = (unsigned short)l0; d.nlc = (unsigned short)lines;
+              out[n] = d;
+            }
+            n++;
+            g0 += items;
+            items = 0;
+            lines = 0;
+          }
+          if (!lines) l0 = l;
+          const unsigned take = min(left, T - items);
+          items += take;
+          lines++;
+          left -= take;
+        }
+      }
+      if (items) {
+        if (FILL) {
+          TileDesc d;
+          d.ray = ray; d.g0 = g0; d.g1 = g0 + items; d.l0 = (unsigned short)l0; d.nlc = (unsigned short)lines;
+          out[n] = d;
+        }
+        n++;
+      }
+    }
   }
-  P.ncta[ray] = n;
+  if (!FILL) P.ncta[ray] = n;
 }
 
 // the rare case of telescope.F:583: the row's continuum is exactly zero, so the reference integrates
@@ -1198,8 +1183,9 @@ void launch_span(const RenderParams &P, cudaStream_t st) {
   if (P.nonredundant) mask_kernel<<<(unsigned)((P.ncell * 4 + 255) / 256), 256, 0, st>>>(P);
   span_kernel<<<(unsigned)P.nray, kSpanThreads, 0, st>>>(P);
 }
-void launch_plan(const RenderParams &P, cudaStream_t st) {
-  plan_kernel<<<(P.nray + 1 + 255) / 256, 256, 0, st>>>(P);
+void launch_plan(const RenderParams &P, bool fill, cudaStream_t st) {
+  if (fill) plan_kernel<true><<<(P.nray + 1 + 127) / 128, 128, 0, st>>>(P);
+  else plan_kernel<false><<<(P.nray + 1 + 127) / 128, 128, 0, st>>>(P);
 }
 // dynamic shared memory per tile_kernel block: 20 warps per SM stay resident next to the 14 KB of
 // exp tables and item metadata each block carries (5 x 128 or 10 x 64 threads)
@@ -1213,9 +1199,11 @@ int tile_smem_limit(int threads) {
   }
   return threads == 128 ? want128 : want64;
 }
-// most lines a tile may span so that two buffers of two slots fit the budget
+// most lines a tile may span so that two buffers of three slots (+ the phantom) fit the budget
 int tile_max_lines(int threads) {
-  return (tile_smem_limit(threads) / 4 - kSlotBytes) / kPairBytes;
+  const int per_buf = tile_smem_limit(threads) / 2;
+  // 3 slots of (kPairBytes nlc + kSlotBytes) + phantom (sizeof(HotLine) nlc + sizeof(HotNode))
+  return (per_buf - 3 * kSlotBytes - (int)sizeof(HotNode)) / (3 * kPairBytes + (int)sizeof(HotLine));
 }
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
   center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);

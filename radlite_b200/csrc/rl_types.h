@@ -85,6 +85,14 @@ struct LineDev {
   double kia;  // sqrt(2^18/ln 2) / k_aa: scaled reciprocal Doppler width per unit 1/width (tile_kernel)
 };
 
+// one tile_kernel block: items [g0, g1) of ray `ray`'s item list, which belong to the nlc lines
+// l0 .. l0+nlc-1 of the batch
+struct __align__(16) TileDesc {
+  int ray;
+  unsigned g0, g1;
+  unsigned short l0, nlc;
+};
+
 // per cell, one bit per line of the batch: N_up + N_down surely above / surely below LEVTHRES
 struct __align__(16) CellMask {
   uint4 on, off;
@@ -117,7 +125,9 @@ struct RenderParams {
   unsigned int *ncta;        // [nray+1] thread blocks of tile_kernel per ray
   const unsigned int *cta_off;   // [nray+1] exclusive scan of ncta
   int smem_budget;           // dynamic shared memory per tile_kernel block [bytes]
-  int tile_threads;          // threads per tile_kernel block (64 or 128); a tile = tile_threads * kTileIpt items
+  int tile_threads;          // threads per tile_kernel block (64 or 128) = most items of a tile
+  int tile_max_lines;        // most lines a tile may span (shared-memory stage)
+  TileDesc *tiles;           // [total tiles] written by plan_kernel<true>
   CellMask *masks;           // [ncell]
   int sparse;                // 1: skipped channels are not materialised in img (spectrum only)
   unsigned char *dense;      // [ntask] sparse mode: row was completed by fill_kernel
