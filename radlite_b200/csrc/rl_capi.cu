@@ -683,7 +683,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
       L.c_src = 5.27296241956e-28 * L.nu0 * L.aud;    // line.F:4571
       L.c_alp = 5.27296241956e-28 * L.nu0;            // line.F:4584
       L.inv_nu0 = 1.0 / L.nu0;
-      L.kia = 614.9746732986623 / L.k_aa;  // sqrt(2^18/ln 2) / k_aa
+      L.kia = 19.217958540583197 / L.k_aa;  // sqrt(256/ln 2) / k_aa
       if (c->out_itype == 2) {  // telescope.F:3996-4000
         const double f = c->linefreq[il];
         L.i_outer = 1.47455253991e-47 * (f * f * f) / (std::exp(4.7991598e-11 * f / kTempCmb) - 1.0);

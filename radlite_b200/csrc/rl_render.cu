@@ -450,17 +450,20 @@ __device__ __forceinline__ long long img_row(const RenderParams &P, int ray) {
 //     candidates) take a separate reference-ordered path.
 //
 // Arithmetic notes (all deviations from the reference are << the 1e-6 tolerance):
-//   exp(x), x <= 0: n = round(x 2^18/ln2), exp = 2^(n>>18) T1[(n>>9)&511] T2[n&511] (1 + r), with
-//   two 512-entry shared-memory tables and |r| <= ln2/2^19; (1 + r) = e^r to r^2/2 < 9e-13 for the
-//   line profile, 1 + r + r^2/2 for exp(-dtau).  The Gaussian argument is carried pre-scaled so
-//   that n and r fall out of two FMAs.  Profile values below
-//   exp(-345) are flushed to 0.  Divisions: hardware reciprocal seed + two Newton steps (< 2e-11).
+//   exp(x), x <= 0: n = round(x 256/ln2), exp = 2^(n>>8) T1[n&255] P(r), with one 256-entry
+//   shared-memory table and |r| <= ln2/512; P = cubic for the line profile (< 1.5e-13), quartic for
+//   exp(-dtau) (< 4e-17).  The Gaussian argument is carried pre-scaled so that n and r fall out of
+//   two FMAs.  Profile values below exp(-345) are flushed to 0.  Divisions: hardware reciprocal seed
+//   + two Newton steps (< 2e-11).
 // ------------------------------------------------------------------------------------------
 constexpr double kExpMagic = 6755399441055744.0;       // 1.5 * 2^52
-constexpr double kLog2eS = 378193.8487987964;          // 2^18 / ln 2
-constexpr double kLn2S = 2.6441466543577014e-06;       // ln 2 / 2^18
-constexpr double kCnorm = 0.0009174293836097514;       // 0.56419583546 / sqrt(2^18 / ln 2)
-constexpr unsigned kHiUmax = 0x40c64f52u;              // hi word of sqrt(345 * 2^18/ln 2): exp(-345) ~ 1e-150
+constexpr double kLog2eS = 369.3299304675746;          // 256 / ln 2
+constexpr double kLn2S = 0.0027076061740622863;        // L = ln 2 / 256
+constexpr double kLn2S2 = 3.6655655969101062e-06;      // L^2 / 2
+constexpr double kLn2S3 = 3.3083026805413713e-09;      // L^3 / 6
+constexpr double kLn2S4 = 2.239395190875157e-12;       // L^4 / 24
+constexpr double kCnorm = 0.029357740275512044;        // 0.56419583546 / sqrt(256 / ln 2)
+constexpr unsigned kHiUmax = 0x40764f52u;              // hi word of sqrt(345 * 256/ln 2): exp(-345) ~ 1e-150
 constexpr unsigned kHiTauMax = 0x40859000u;            // hi word of 690.0
 constexpr double kAlpTiny = 1.0e-280;                  // alpha <= this is treated like alpha <= 0
 
@@ -513,27 +516,28 @@ __device__ __forceinline__ double div_fast(double n, double x) {
   return fma(q, e, q);
 }
 
-// 2^(n / 2^18) e^r, r = rp ln2/2^18: the table part of exp (see header).  T1, T2 = shared-window
-// addresses of the two tables.  QUAD = false: e^r ~ 1 + r (relative error < 9e-13, the line profile);
-// QUAD = true: 1 + r + r^2/2 (full double precision: exp(-dtau) feeds the cancelling differences
-// e0 = 1 - xp, e1 = dtau - e0 of transfer.F:1519-1520, whose error is the absolute error of xp).
-template <bool QUAD>
-__device__ __forceinline__ double exp_tab(double t, double rp, uint32_t T1, uint32_t T2) {
+// 2^(n / 256) e^r, r = rp ln2/256, |rp| <= 1/2: one 256-entry table of 2^(j/256) (a single 8-byte
+// shared-memory read per exp: the LSU data pipe, not the FP64 pipe, was the limiter with larger
+// tables) and a short polynomial.  DEG = 3: relative error r^4/24 < 1.5e-13 (the line profile);
+// DEG = 4: r^5/120 < 4e-17 (exp(-dtau) feeds the cancelling differences e0 = 1 - xp, e1 = dtau - e0
+// of transfer.F:1519-1520, whose error is the absolute error of xp).  T1 = shared-window address.
+template <int DEG>
+__device__ __forceinline__ double exp_tab(double t, double rp, uint32_t T1) {
   const int n = __double2loint(t);
-  const double2 w = lds_f64x2(T2 + ((n << 4) & 0x1ff0));
-  const double v = lds_f64(T1 + ((n >> 6) & 0xff8));
-  double inner;
-  if (QUAD) inner = fma(w.y * rp, fma(rp, 0.5 * kLn2S, 1.0), w.x);
-  else inner = fma(w.y, rp, w.x);
-  const int hi = __double2hiint(v) + ((n >> 18) << 20);
-  return __hiloint2double(hi, __double2loint(v)) * inner;
+  const double v = lds_f64(T1 + ((n << 3) & 0x7f8));
+  double p = (DEG == 4) ? fma(rp, kLn2S4, kLn2S3) : kLn2S3;
+  p = fma(p, rp, kLn2S2);
+  p = fma(p, rp, kLn2S);
+  p = fma(p, rp, 1.0);
+  const int hi = __double2hiint(v) + ((n >> 8) << 20);
+  return __hiloint2double(hi, __double2loint(v)) * p;
 }
-// exp(-u^2 ln2/2^18) for the pre-scaled argument u; exactly 0 beyond exp(-345)
+// exp(-u^2 ln2/256) for the pre-scaled argument u; exactly 0 beyond exp(-345)
 __device__ __forceinline__ double gauss_tab(double u, uint32_t T1, uint32_t T2) {
   const double t = fma(-u, u, kExpMagic);
   const double fn = t - kExpMagic;
   const double rp = fma(-u, u, -fn);
-  const double e = exp_tab<false>(t, rp, T1, T2);
+  const double e = exp_tab<3>(t, rp, T1);
   const bool far = ((unsigned)__double2hiint(u) & 0x7fffffffu) > kHiUmax;
   return far ? 0.0 : e;
 }
@@ -544,7 +548,7 @@ __device__ __forceinline__ double expneg_tab(double d, uint32_t T1, uint32_t T2)
   const double t = fma(dc, -kLog2eS, kExpMagic);
   const double fn = t - kExpMagic;
   const double rp = fma(dc, -kLog2eS, -fn);
-  return exp_tab<true>(t, rp, T1, T2);
+  return exp_tab<4>(t, rp, T1);
 }
 
 // the qdr_src_2 step (transfer.F:1498-1571) with all case selections branch free; r0 = src0/alp0
@@ -615,8 +619,7 @@ __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch,
 
 // per-block tables and per-item metadata of tile_kernel (file scope: the out-of-line slow path uses
 // them too)
-__shared__ double s_T1[512];         // 2^(j/512)
-__shared__ double2 s_T2[512];        // {2^(j/2^18), 2^(j/2^18) ln2/2^18}
+__shared__ double s_T1[256];         // 2^(j/256)
 __shared__ int2 s_meta[128];      // {line slot, channel | cmask bit} of the thread's item
 __shared__ unsigned s_flags[128]; // maser | extra elements << 8 of the thread's item
 __shared__ double s_dnu[128];     // line_dnu of the thread's item
@@ -633,7 +636,7 @@ __device__ __noinline__ unsigned slow_step(double *st, TileBuf B, int nlc, int s
                                            const double *__restrict__ star_line, int nfr, double starfract) {
   double inten = st[0], src0 = st[1], alp0 = st[2], r0;
   unsigned ret = 0;
-  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1), T2 = (uint32_t)__cvta_generic_to_shared(s_T2);
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1), T2 = 0;
   const uint32_t fl = smem_ptr<HotNode>(B.hn)[slot].flags;
   const ColdNode c1 = smem_ptr<ColdNode>(B.cn)[slot], c0 = smem_ptr<ColdNode>(B.cn)[slot - 1];
   const HotLine h1 = smem_ptr<HotLine>(B.hl)[slot * nlc + ml], h0 = smem_ptr<HotLine>(B.hl)[(slot - 1) * nlc + ml];
@@ -693,49 +696,152 @@ __device__ __noinline__ unsigned slow_step(double *st, TileBuf B, int nlc, int s
   st[3] = r0;
   return ret;
 }
-template <int NT>
-__device__ __noinline__ void stage_chunk(const RenderParams &P, const TileBuf &B, int nlc, int l0,
-                                            long long n0, int c0, int cnt, int tid) {
-  const int npair = (cnt + 1) * nlc;
-  for (int p = tid; p < npair; p += NT) {
-    const int slot = p / nlc, m = p - slot * nlc;
-    const int node = c0 - 1 + slot;
-    const Node nd = load_node(P.nodes.rec, n0 + node);
+// named barriers of tile_kernel (0 is __syncthreads): "buffer b holds a staged chunk" and "buffer b
+// has been consumed"
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+constexpr int kTileBufs = 3;        // staged chunks in flight
+constexpr int kProducerThreads = 32;  // one staging warp per block
+
+// ---- producer side of tile_kernel -----------------------------------------------------------
+// per-tile line constants and the node records of the chunk being staged / the next one
+struct __align__(16) LineC {
+  double c_src, c_alp, bud, bdu, nu0, kia;
+};
+constexpr int kMaxTileLines = 64;
+__shared__ LineC s_linec[kMaxTileLines];
+__shared__ NodeRec s_nodes[2][32];
+
+// the global loads one (node, line) pair needs up front: two stencil cells (extra points, crossing
+// type 3, fetch their other two when interpolating)
+struct PairLoads {
+  double4 a, b;
+};
+__device__ __forceinline__ PairLoads pair_issue(const double4 *__restrict__ cellL, const NodeRec *nd) {
+  PairLoads L;
+  const int icr = (int)(((uint32_t)nd->cells.x >> kCellFlagShift) & kFlagIcrMask);
+  L.a = ldg4(cellL + (nd->cells.x & kCellMask));
+  L.b = ldg4(cellL + (icr == 2 ? nd->cells.z : nd->cells.y));
+  return L;
+}
+// line.F:4054-4197 (same expressions as gather_line)
+__device__ __forceinline__ double4 pair_interp(const PairLoads &L, const double4 *__restrict__ cellL,
+                                               const NodeRec *nd) {
+  const int icr = (int)(((uint32_t)nd->cells.x >> kCellFlagShift) & kFlagIcrMask);
+  double4 o;
+  if (icr != 3) {
+    const double w = (icr == 2) ? nd->wr : nd->wt;
+    o.x = (1.0 - w) * L.a.x + w * L.b.x;
+    o.y = (1.0 - w) * L.a.y + w * L.b.y;
+    o.z = (1.0 - w) * L.a.z + w * L.b.z;
+    o.w = (1.0 - w) * L.a.w + w * L.b.w;
+  } else {
+    const double4 c = ldg4(cellL + nd->cells.z), d = ldg4(cellL + nd->cells.w);
+    const double dr = nd->wr, dt = nd->wt;
+    o.x = (1.0 - dr) * ((1.0 - dt) * L.a.x + dt * L.b.x) + dr * ((1.0 - dt) * c.x + dt * d.x);
+    o.y = (1.0 - dr) * ((1.0 - dt) * L.a.y + dt * L.b.y) + dr * ((1.0 - dt) * c.y + dt * d.y);
+    o.z = (1.0 - dr) * ((1.0 - dt) * L.a.z + dt * L.b.z) + dr * ((1.0 - dt) * c.z + dt * d.z);
+    o.w = (1.0 - dr) * ((1.0 - dt) * L.a.w + dt * L.b.w) + dr * ((1.0 - dt) * c.w + dt * d.w);
+  }
+  return o;
+}
+__device__ __forceinline__ void pair_store(const TileBuf &B, int p, int slot, int m, int node,
+                                           const NodeRec *chunk_nodes, const double4 v, int subgrid) {
+  const NodeRec &nd = chunk_nodes[slot];
+  const LineC lc = s_linec[m];
+  ColdLine c;
+  c.cN = lc.c_src * v.z;
+  c.kk = lc.c_alp * (v.w * lc.bdu - v.z * lc.bud);
+  HotLine h;
+  h.srcd = v.x;
+  h.alpd = v.y;
+  h.ia = nd.inv_lwav * lc.kia;
+  h.nv = (lc.nu0 * nd.dvmu) * h.ia;
+  const double norm = kCnorm * h.ia;
+  h.A1 = c.cN * norm;
+  h.K1 = c.kk * norm;
+  smem_ptr<HotLine>(B.hl)[p] = h;
+  smem_ptr<ColdLine>(B.cl)[p] = c;
+  if (m == 0) {
+    HotNode a;
+    a.hds = 0.5 * nd.ds;
+    uint32_t fl = ((uint32_t)nd.cells.x >> kCellFlagShift) & ~kFlagIcrMask;
+    if (!subgrid) fl &= ~kFlagSub;
+    if (node == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
+    a.flags = fl;
+    a.pad = 0;
+    smem_ptr<HotNode>(B.hn)[slot] = a;
+    ColdNode b;
+    // mean width of the segment ending here (slot 0 only serves as a start point: never read)
+    const double lw_prev = (slot > 0) ? chunk_nodes[slot - 1].lw : nd.lw;
+    b.ds = nd.ds;
+    b.dvmu = nd.dvmu;
+    b.lwav = 0.5 * (lw_prev + nd.lw);
+    b.pad = 0.0;
+    smem_ptr<ColdNode>(B.cn)[slot] = b;
+  }
+}
+
+// the producer warp: stages chunk after chunk (nodes c0-1 .. c0+cnt-1 -> slots 0 .. cnt) into the
+// buffer ring.  Node records are fetched one chunk ahead (one per lane, coalesced) and parked in
+// shared memory; every lane then handles two (node, line) pairs at a time with all their gathers in
+// flight together.
+__device__ __noinline__ void producer_loop(const RenderParams &P, uint32_t smem0, int bufbytes, int nch,
+                                           int nlc, int l0, long long n0, int N, int nchunks, int lane,
+                                           int nall) {
+  for (int m = lane; m < nlc; m += 32) {
     const LineDev *Lm = P.lines + (l0 + m);
-    const double4 v = gather_line(P.cellL + (size_t)(l0 + m) * P.ncell, nd.cells, nd.wr, nd.wt,
-                                  nd.flags & kFlagIcrMask);
-    const double c_src = __ldg(&Lm->c_src), c_alp = __ldg(&Lm->c_alp), bud = __ldg(&Lm->bud),
-                 bdu = __ldg(&Lm->bdu), nu0 = __ldg(&Lm->nu0), kia = __ldg(&Lm->kia);
-    ColdLine c;
-    c.cN = c_src * v.z;
-    c.kk = c_alp * (v.w * bdu - v.z * bud);
-    HotLine h;
-    h.srcd = v.x;
-    h.alpd = v.y;
-    h.ia = nd.inv_lwav * kia;
-    h.nv = (nu0 * nd.dvmu) * h.ia;
-    const double norm = kCnorm * h.ia;
-    h.A1 = c.cN * norm;
-    h.K1 = c.kk * norm;
-    smem_ptr<HotLine>(B.hl)[p] = h;
-    smem_ptr<ColdLine>(B.cl)[p] = c;
-    if (m == 0) {
-      HotNode a;
-      a.hds = 0.5 * nd.ds;
-      uint32_t fl = nd.flags & ~kFlagIcrMask;
-      if (!P.subgrid) fl &= ~kFlagSub;
-      if (node == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
-      a.flags = fl;
-      a.pad = 0;
-      smem_ptr<HotNode>(B.hn)[slot] = a;
-      ColdNode b;
-      const double lw_prev = (node > 0) ? __ldg(&P.nodes.rec[n0 + node - 1].lw) : nd.lw;
-      b.ds = nd.ds;
-      b.dvmu = nd.dvmu;
-      b.lwav = 0.5 * (lw_prev + nd.lw);
-      b.pad = 0.0;
-      smem_ptr<ColdNode>(B.cn)[slot] = b;
+    LineC lc;
+    lc.c_src = __ldg(&Lm->c_src); lc.c_alp = __ldg(&Lm->c_alp); lc.bud = __ldg(&Lm->bud);
+    lc.bdu = __ldg(&Lm->bdu); lc.nu0 = __ldg(&Lm->nu0); lc.kia = __ldg(&Lm->kia);
+    s_linec[m] = lc;
+  }
+  const NodeRec *rec = P.nodes.rec + n0;
+  // node records travel global -> shared without passing through registers (cp.async, 4 x 16 B)
+  auto fetch_nodes = [&](int buf, int first, int count) {
+    if (lane < count) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_nodes[buf][lane]);
+      const char *src = reinterpret_cast<const char *>(rec + first + lane);
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * k), "l"(src + 16 * k) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch_nodes(0, 0, min(nch, N - 1) + 1);
+  for (int c = 0, b = 0; c < nchunks; c++, b = (b + 1 == kTileBufs) ? 0 : b + 1) {
+    const int c0 = 1 + c * nch, cnt = min(nch, N - c0);
+    // this chunk's node records have landed; the next chunk's go in flight while this one is staged
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    const int c0n = c0 + nch;
+    if (c + 1 < nchunks) fetch_nodes((c + 1) & 1, c0n - 1, min(nch, N - c0n) + 1);
+    if (c >= kTileBufs) bar_sync(1 + kTileBufs + b, nall);  // empty[b]
+    TileBuf B;
+    B.hn = smem0 + (uint32_t)(b * bufbytes);
+    B.hl = B.hn + (uint32_t)((nch + 2) * sizeof(HotNode));
+    B.cn = B.hl + (uint32_t)((nch + 2) * nlc * sizeof(HotLine));
+    B.cl = B.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
+    const NodeRec *cn = s_nodes[c & 1];
+    const int npair = (cnt + 1) * nlc;
+    for (int p = lane; p < npair; p += 64) {
+      const int pA = p, pB = p + 32;
+      const bool hasB = pB < npair;
+      const int slotA = pA / nlc, mA = pA - slotA * nlc;
+      const int slotB = hasB ? pB / nlc : slotA, mB = hasB ? pB - slotB * nlc : mA;
+      const double4 *cellA = P.cellL + (size_t)(l0 + mA) * P.ncell, *cellB = P.cellL + (size_t)(l0 + mB) * P.ncell;
+      const PairLoads LA = pair_issue(cellA, cn + slotA);
+      const PairLoads LB = pair_issue(cellB, cn + slotB);
+      pair_store(B, pA, slotA, mA, c0 - 1 + slotA, cn, pair_interp(LA, cellA, cn + slotA), P.subgrid);
+      if (hasB) pair_store(B, pB, slotB, mB, c0 - 1 + slotB, cn, pair_interp(LB, cellB, cn + slotB), P.subgrid);
+    }
+    __threadfence_block();
+    __syncwarp();
+    bar_arrive(1 + b, nall);  // full[b]
   }
 }
 
@@ -769,7 +875,7 @@ __device__ __forceinline__ PreSlot pre_slot(uint32_t an, uint32_t ah, double dnu
 // item state is re-materialised after such a call (manual live-range splitting).
 __device__ __forceinline__ void integrate_chunk(const RenderParams &P, const TileBuf B, int nlc, int cnt,
                                                 Item &it, int l0, int &r0ok) {
-  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1), T2 = (uint32_t)__cvta_generic_to_shared(s_T2);
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1), T2 = 0;
   int slot = 1;
   while (slot <= cnt) {
     const uint32_t stride = (uint32_t)nlc * (uint32_t)sizeof(HotLine);
@@ -832,18 +938,48 @@ __device__ __forceinline__ void integrate_chunk(const RenderParams &P, const Til
   }
 }
 
+// Block = NT consumer threads (one (line, channel) item each, threads 0..NT-1) + one producer warp.
+// The producer gathers, interpolates and stages chunk after chunk of the ray's nodes into a ring of
+// kTileBufs shared-memory buffers; the consumers never touch global memory inside the ray loop (the
+// flagged-node path excepted).  Hand-over by named barriers: full[b] (producer arrives, consumers
+// wait) and empty[b] (consumers arrive, producer waits).
 template <int NT>
-__global__ void __launch_bounds__(NT, 640 / NT) tile_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(NT + kProducerThreads, 512 / NT)
+    tile_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ double4 smem_raw[];
+  constexpr int NALL = NT + kProducerThreads;
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int j = tid; j < 512; j += NT) {
-    s_T1[j] = exp2((double)j * (1.0 / 512.0));
-    const double w = exp2((double)j * (1.0 / 262144.0));
-    s_T2[j] = make_double2(w, w * kLn2S);
-  }
+  for (int j = tid; j < 256; j += NALL) s_T1[j] = exp2((double)j * (1.0 / 256.0));
   const TileDesc td = P.tiles[blockIdx.x];
   const int ray = td.ray, l0 = td.l0, nlc = td.nlc;
   const unsigned g0 = td.g0, g1 = td.g1;
+  const long long n0 = P.node_off[ray];
+  const int N = (int)(P.node_off[ray + 1] - n0);
+  // shared-memory carve-up: kTileBufs buffers of nch+1 slots (+1 phantom slot of hn and hl, see
+  // integrate_chunk)
+  const int slot_bytes = nlc * kPairBytes + kSlotBytes, ph_bytes = nlc * (int)sizeof(HotLine) + (int)sizeof(HotNode);
+  int nch = (P.smem_budget / kTileBufs - ph_bytes) / slot_bytes - 1;
+  nch = max(1, min(kTileChunk, nch));
+  const int bufbytes = (nch + 1) * slot_bytes + ph_bytes;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  auto make_buf = [&](int b) {
+    TileBuf t;
+    t.hn = smem0 + (uint32_t)(b * bufbytes);
+    t.hl = t.hn + (uint32_t)((nch + 2) * sizeof(HotNode));
+    t.cn = t.hl + (uint32_t)((nch + 2) * nlc * sizeof(HotLine));
+    t.cl = t.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
+    return t;
+  };
+  const int nchunks = (N > 1) ? (N - 1 + nch - 1) / nch : 0;
+
+  if (tid >= NT) {
+    // ---------------- producer warp ----------------
+    __syncthreads();  // (exp tables; keeps the barrier-0 count uniform)
+    producer_loop(P, smem0, bufbytes, nch, nlc, l0, n0, N, nchunks, lane, NALL);
+    return;
+  }
+
+  // ---------------- consumers ----------------
   // my item: g0 + tid; surplus threads shadow the tile's first item and store nothing
   Item it;
   {
@@ -866,37 +1002,13 @@ __global__ void __launch_bounds__(NT, 640 / NT) tile_kernel(const __grid_constan
     it.inten = (P.out_itype == 3) ? P.isrf_line[(size_t)a * P.nfr + ch] : P.lines[a].i_outer;
     it.src0 = it.alp0 = it.r0 = 0.0;
   }
-  const long long n0 = P.node_off[ray];
-  const int N = (int)(P.node_off[ray + 1] - n0);
-  // shared-memory carve-up: two buffers of nch+1 slots (+1 phantom slot of hn and hl, see
-  // integrate_chunk)
-  const int slot_bytes = nlc * kPairBytes + kSlotBytes, ph_bytes = nlc * (int)sizeof(HotLine) + (int)sizeof(HotNode);
-  int nch = (P.smem_budget / 2 - ph_bytes) / slot_bytes - 1;
-  nch = max(1, min(kTileChunk, nch));
-  const int bufbytes = (nch + 1) * slot_bytes + ph_bytes;
-  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  auto make_buf = [&](int b) {
-    TileBuf t;
-    t.hn = smem0 + (uint32_t)(b * bufbytes);
-    t.hl = t.hn + (uint32_t)((nch + 2) * sizeof(HotNode));
-    t.cn = t.hl + (uint32_t)((nch + 2) * nlc * sizeof(HotLine));
-    t.cl = t.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
-    return t;
-  };
   int r0ok = 0;
   __syncthreads();  // exp tables
-  if (N > 1) {
-    stage_chunk<NT>(P, make_buf(0), nlc, l0, n0, 1, min(nch, N - 1), tid);
-    __syncthreads();
-    int cur = 0;
-    for (int c0 = 1; c0 < N; c0 += nch, cur ^= 1) {
-      const int cnt = min(nch, N - c0);
-      const int c1 = c0 + nch;
-      if (c1 < N) stage_chunk<NT>(P, make_buf(cur ^ 1), nlc, l0, n0, c1, min(nch, N - c1), tid);
-      const TileBuf Bc = make_buf(cur);
-      integrate_chunk(P, Bc, nlc, cnt, it, l0, r0ok);
-      __syncthreads();
-    }
+  for (int c = 0, b = 0; c < nchunks; c++, b = (b + 1 == kTileBufs) ? 0 : b + 1) {
+    bar_sync(1 + b, NALL);  // full[b]
+    const int c0 = 1 + c * nch;
+    integrate_chunk(P, make_buf(b), nlc, min(nch, N - c0), it, l0, r0ok);
+    if (c + kTileBufs < nchunks) bar_arrive(1 + kTileBufs + b, NALL);  // empty[b]
   }
   unsigned long long r = 0, x = 0;
   if (g0 + tid < g1) {
@@ -1187,11 +1299,11 @@ void launch_plan(const RenderParams &P, bool fill, cudaStream_t st) {
   if (fill) plan_kernel<true><<<(P.nray + 1 + 127) / 128, 128, 0, st>>>(P);
   else plan_kernel<false><<<(P.nray + 1 + 127) / 128, 128, 0, st>>>(P);
 }
-// dynamic shared memory per tile_kernel block: 20 warps per SM stay resident next to the 14 KB of
-// exp tables and item metadata each block carries (5 x 128 or 10 x 64 threads)
+// dynamic shared memory per tile_kernel block: 4 blocks of 128+32 threads (8 of 64+32) per SM, next
+// to the 12 KB of exp table, node / line scratch and item metadata each block carries
 int tile_smem_limit(int threads) {
   static int done = 0;
-  const int want128 = 29 * 1024, want64 = 7 * 1024;
+  const int want128 = 44 * 1024, want64 = 15 * 1024;
   if (!done) {
     cudaFuncSetAttribute(tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, want128);
     cudaFuncSetAttribute(tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, want64);
@@ -1199,17 +1311,17 @@ int tile_smem_limit(int threads) {
   }
   return threads == 128 ? want128 : want64;
 }
-// most lines a tile may span so that two buffers of three slots (+ the phantom) fit the budget
+// most lines a tile may span so that kTileBufs buffers of three slots (+ the phantom) fit the budget
 int tile_max_lines(int threads) {
-  const int per_buf = tile_smem_limit(threads) / 2;
+  const int per_buf = tile_smem_limit(threads) / kTileBufs;
   // 3 slots of (kPairBytes nlc + kSlotBytes) + phantom (sizeof(HotLine) nlc + sizeof(HotNode))
-  return (per_buf - 3 * kSlotBytes - (int)sizeof(HotNode)) / (3 * kPairBytes + (int)sizeof(HotLine));
+  return min(kMaxTileLines, (per_buf - 3 * kSlotBytes - (int)sizeof(HotNode)) / (3 * kPairBytes + (int)sizeof(HotLine)));
 }
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
   center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);
   if (!total_ctas) return;
-  if (P.tile_threads == 128) tile_kernel<128><<<total_ctas, 128, P.smem_budget, st>>>(P);
-  else tile_kernel<64><<<total_ctas, 64, P.smem_budget, st>>>(P);
+  if (P.tile_threads == 128) tile_kernel<128><<<total_ctas, 128 + kProducerThreads, P.smem_budget, st>>>(P);
+  else tile_kernel<64><<<total_ctas, 64 + kProducerThreads, P.smem_budget, st>>>(P);
 }
 void launch_fill(const RenderParams &P, cudaStream_t st) {
   if (!P.nonredundant) return;  // every channel was integrated

@@ -14,7 +14,7 @@ constexpr int kRayRnpt = 4;
 constexpr int kMaxExtra = 40;  // 2 + 4*RAYADPT*2 = 34 used
 constexpr int kLgNrMax = 31;   // line.F:4657-4661
 constexpr int kTileIpt = 1;        // ray-channel items per tile_kernel thread
-constexpr int kTileChunk = 32;     // nodes staged in shared memory per pass (upper bound)
+constexpr int kTileChunk = 31;     // nodes staged per chunk (upper bound: chunk + 1 previous node = one per producer lane)
 constexpr int kSpanThreads = 128;  // span_kernel block = lines per batch upper bound (one mask bit per line)
 
 // node flags (low 2 bits = tr_icross: 1 = R crossing, 2 = theta crossing, 3 = extra point)
