@@ -51,23 +51,24 @@ __device__ __forceinline__ Node load_node(const NodeRec *__restrict__ rec, long 
 
 // interpolate the per-line cell record {src_dust, alp_dust, N_up, N_down} at a node
 // (line.F:4054-4197; three cases by crossing type)
-__device__ __forceinline__ double4 gather_line(const double4 *__restrict__ cellL, int4 c, double dr,
-                                               double dt, int icr) {
-  double4 a = ldg4(cellL + c.x), o;
+__device__ __forceinline__ double4 gather_line(const double4 *__restrict__ cellL, size_t nl, int4 c,
+                                               double dr, double dt, int icr) {
+  // cell-major layout: record of line l at cell k is cellL[k * nl + l]; cellL points at line l of cell 0
+  double4 a = ldg4(cellL + (size_t)c.x * nl), o;
   if (icr == 1) {
-    double4 b = ldg4(cellL + c.y);
+    double4 b = ldg4(cellL + (size_t)c.y * nl);
     o.x = (1.0 - dt) * a.x + dt * b.x;
     o.y = (1.0 - dt) * a.y + dt * b.y;
     o.z = (1.0 - dt) * a.z + dt * b.z;
     o.w = (1.0 - dt) * a.w + dt * b.w;
   } else if (icr == 2) {
-    double4 b = ldg4(cellL + c.z);
+    double4 b = ldg4(cellL + (size_t)c.z * nl);
     o.x = (1.0 - dr) * a.x + dr * b.x;
     o.y = (1.0 - dr) * a.y + dr * b.y;
     o.z = (1.0 - dr) * a.z + dr * b.z;
     o.w = (1.0 - dr) * a.w + dr * b.w;
   } else {
-    double4 b = ldg4(cellL + c.y), cc = ldg4(cellL + c.z), d = ldg4(cellL + c.w);
+    double4 b = ldg4(cellL + (size_t)c.y * nl), cc = ldg4(cellL + (size_t)c.z * nl), d = ldg4(cellL + (size_t)c.w * nl);
     o.x = (1.0 - dr) * ((1.0 - dt) * a.x + dt * b.x) + dr * ((1.0 - dt) * cc.x + dt * d.x);
     o.y = (1.0 - dr) * ((1.0 - dt) * a.y + dt * b.y) + dr * ((1.0 - dt) * cc.y + dt * d.y);
     o.z = (1.0 - dr) * ((1.0 - dt) * a.z + dt * b.z) + dr * ((1.0 - dt) * cc.z + dt * d.z);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) prep_cells_kernel(PrepParams P) {
   o.y = alp;
   o.z = pp[P.lev_up[l] - 1] * ab * rh * P.molpg;
   o.w = pp[P.lev_down[l] - 1] * ab * rh * P.molpg;
-  P.cellL[(size_t)l * P.ncell + cell] = o;
+  P.cellL[(size_t)cell * P.nl + l] = o;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) mask_kernel(RenderParams P) {
   for (int b = 0; b < 32; b++) {
     const int l = 32 * w + b;
     if (l < P.nl) {
-      const double2 zw = __ldg(reinterpret_cast<const double2 *>(P.cellL + (size_t)l * P.ncell + cell) + 1);
+      const double2 zw = __ldg(reinterpret_cast<const double2 *>(P.cellL + (size_t)cell * P.nl + l) + 1);
       const double s = zw.x + zw.y;
       on |= (s > hi ? 1u : 0u) << b;
       off |= (s < lo ? 1u : 0u) << b;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
     return;
   }
   const long long n0 = P.node_off[ray], n1 = P.node_off[ray + 1];
-  const double4 *cellL = P.cellL + (size_t)l * P.ncell;
+  const double4 *cellL = P.cellL + l;
   const int w = (l >> 5) & 3;
   const uint32_t bit = 1u << (l & 31);
   double vmin = 2.0, vmax = -2.0;
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
           bool in = (o & bit) != 0;
           if (!in) {  // stencil cells disagree (or sit on the threshold): evaluate the interpolation
             const Node nd = load_node(P.nodes.rec, c + t);
-            const double4 v = gather_line(cellL, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
+            const double4 v = gather_line(cellL, (size_t)P.nl, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
             in = v.z + v.w > P.levthres;
           }
           if (in) {
@@ -376,7 +377,7 @@ __device__ __noinline__ int subgrid_segment(const LineDev &L, double dnu_ch, dou
 __device__ __noinline__ double integrate_ray_channel(const RenderParams &P, int l, int ray, int ch,
                                                      double &tau, unsigned &nelem, int &maser) {
   const LineDev L = P.lines[l];
-  const double4 *__restrict__ cellL = P.cellL + (size_t)l * P.ncell;
+  const double4 *__restrict__ cellL = P.cellL + l;
   const long long n0 = P.node_off[ray], n1 = P.node_off[ray + 1];
   const double dnu_ch = P.line_dnu[(size_t)l * P.nfr + ch];
   const double velo_ch = dnu_ch / L.nu0;
@@ -388,13 +389,13 @@ __device__ __noinline__ double integrate_ray_channel(const RenderParams &P, int 
   k.init = 1;
   k.srcl0 = k.alpl0 = 0.0;
   Node nd = load_node(P.nodes.rec, n0);
-  double4 v0 = gather_line(cellL, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
+  double4 v0 = gather_line(cellL, (size_t)P.nl, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
   double dvmu0 = nd.dvmu, lw0 = nd.lw;
   for (long long i = n0 + 1; i < n1; i++) {
     nd = load_node(P.nodes.rec, i);
     const uint32_t fl = nd.flags;
     const double ds = nd.ds, dvmu1 = nd.dvmu, lw1 = nd.lw;
-    const double4 v1 = gather_line(cellL, nd.cells, nd.wr, nd.wt, fl & kFlagIcrMask);
+    const double4 v1 = gather_line(cellL, (size_t)P.nl, nd.cells, nd.wr, nd.wt, fl & kFlagIcrMask);
     if (fl & (kFlagInit | kFlagStar | kFlagZero)) {
       if (fl & kFlagZero) inten = 0.0;
       if (fl & kFlagStar)
@@ -721,15 +722,15 @@ __shared__ NodeRec s_nodes[2][32];
 struct PairLoads {
   double4 a, b;
 };
-__device__ __forceinline__ PairLoads pair_issue(const double4 *__restrict__ cellL, const NodeRec *nd) {
+__device__ __forceinline__ PairLoads pair_issue(const double4 *__restrict__ cellL, size_t nl, const NodeRec *nd) {
   PairLoads L;
   const int icr = (int)(((uint32_t)nd->cells.x >> kCellFlagShift) & kFlagIcrMask);
-  L.a = ldg4(cellL + (nd->cells.x & kCellMask));
-  L.b = ldg4(cellL + (icr == 2 ? nd->cells.z : nd->cells.y));
+  L.a = ldg4(cellL + (size_t)(nd->cells.x & kCellMask) * nl);
+  L.b = ldg4(cellL + (size_t)(icr == 2 ? nd->cells.z : nd->cells.y) * nl);
   return L;
 }
 // line.F:4054-4197 (same expressions as gather_line)
-__device__ __forceinline__ double4 pair_interp(const PairLoads &L, const double4 *__restrict__ cellL,
+__device__ __forceinline__ double4 pair_interp(const PairLoads &L, const double4 *__restrict__ cellL, size_t nl,
                                                const NodeRec *nd) {
   const int icr = (int)(((uint32_t)nd->cells.x >> kCellFlagShift) & kFlagIcrMask);
   double4 o;
@@ -740,7 +741,7 @@ __device__ __forceinline__ double4 pair_interp(const PairLoads &L, const double4
     o.z = (1.0 - w) * L.a.z + w * L.b.z;
     o.w = (1.0 - w) * L.a.w + w * L.b.w;
   } else {
-    const double4 c = ldg4(cellL + nd->cells.z), d = ldg4(cellL + nd->cells.w);
+    const double4 c = ldg4(cellL + (size_t)nd->cells.z * nl), d = ldg4(cellL + (size_t)nd->cells.w * nl);
     const double dr = nd->wr, dt = nd->wt;
     o.x = (1.0 - dr) * ((1.0 - dt) * L.a.x + dt * L.b.x) + dr * ((1.0 - dt) * c.x + dt * d.x);
     o.y = (1.0 - dr) * ((1.0 - dt) * L.a.y + dt * L.b.y) + dr * ((1.0 - dt) * c.y + dt * d.y);
@@ -788,8 +789,8 @@ __device__ __forceinline__ void pair_store(const TileBuf &B, int p, int slot, in
 
 // the producer warp: stages chunk after chunk (nodes c0-1 .. c0+cnt-1 -> slots 0 .. cnt) into the
 // buffer ring.  Node records are fetched one chunk ahead (one per lane, coalesced) and parked in
-// shared memory; every lane then handles two (node, line) pairs at a time with all their gathers in
-// flight together.
+// shared memory; every lane then handles four (node, line) pairs at a time with all their gathers
+// in flight together.
 __device__ __noinline__ void producer_loop(const RenderParams &P, uint32_t smem0, int bufbytes, int nch,
                                            int nlc, int l0, long long n0, int N, int nchunks, int lane,
                                            int nall) {
@@ -828,16 +829,28 @@ __device__ __noinline__ void producer_loop(const RenderParams &P, uint32_t smem0
     B.cl = B.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
     const NodeRec *cn = s_nodes[c & 1];
     const int npair = (cnt + 1) * nlc;
-    for (int p = lane; p < npair; p += 64) {
-      const int pA = p, pB = p + 32;
-      const bool hasB = pB < npair;
-      const int slotA = pA / nlc, mA = pA - slotA * nlc;
-      const int slotB = hasB ? pB / nlc : slotA, mB = hasB ? pB - slotB * nlc : mA;
-      const double4 *cellA = P.cellL + (size_t)(l0 + mA) * P.ncell, *cellB = P.cellL + (size_t)(l0 + mB) * P.ncell;
-      const PairLoads LA = pair_issue(cellA, cn + slotA);
-      const PairLoads LB = pair_issue(cellB, cn + slotB);
-      pair_store(B, pA, slotA, mA, c0 - 1 + slotA, cn, pair_interp(LA, cellA, cn + slotA), P.subgrid);
-      if (hasB) pair_store(B, pB, slotB, mB, c0 - 1 + slotB, cn, pair_interp(LB, cellB, cn + slotB), P.subgrid);
+    // four pairs per lane and round, all their gathers in flight together; consecutive lanes take
+    // consecutive lines of one node: with the cell-major layout their records are contiguous
+    const size_t nl = (size_t)P.nl;
+    const double4 *cell0 = P.cellL + l0;
+    for (int p = lane; p < npair; p += 4 * 32) {
+      int slot[4], m[4];
+      bool has[4];
+      PairLoads L[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int q = p + 32 * k;
+        has[k] = q < npair;
+        slot[k] = has[k] ? q / nlc : 0;
+        m[k] = has[k] ? q - slot[k] * nlc : 0;
+        L[k] = pair_issue(cell0 + m[k], nl, cn + slot[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (has[k])
+          pair_store(B, p + 32 * k, slot[k], m[k], c0 - 1 + slot[k], cn,
+                     pair_interp(L[k], cell0 + m[k], nl, cn + slot[k]), P.subgrid);
+      }
     }
     __threadfence_block();
     __syncwarp();

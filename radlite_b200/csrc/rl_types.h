@@ -110,7 +110,7 @@ struct RenderParams {
   int out_itype;
   const long long *node_off;
   NodesDev nodes;
-  const double4 *cellL;  // [nl][ncell]
+  const double4 *cellL;  // [ncell][nl] (cell-major: the lines of a tile at one cell are contiguous)
   long long ncell;
   const LineDev *lines;      // [nl]
   const double *line_dnu;    // [nl][nfr]
@@ -164,7 +164,7 @@ struct PrepParams {
   const double *freq;    // [nl]
   const double *ld_src;  // [nl][ncell]
   const double *ld_alp;
-  double4 *cellL;        // [nl][ncell]
+  double4 *cellL;        // [ncell][nl]
 };
 
 }  // namespace rl
