@@ -109,6 +109,21 @@ int rl_render(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double 
               double *flux, double *imcir, int *cmask, double *tau_center, int *maserflag,
               double *velo);
 
+/* ---- multi-GPU by camera-ring block (single-line configs) -----------------
+ * The ring loop `do ir=1,nrr` of make_image_circular (telescope.F:532) and the ring sum of
+ * calc_freq_flux_observer (telescope.F:1388-1433) split over ranks: rl_render_rings traces only
+ * the camera rings ring_lo..ring_hi (0 = the central beam telescope.F:498-527, 1..nrr) and returns
+ *   ringsum [nl][nrr+1][nfr]   row 0 = pi ri(1)^2 I_centre (telescope.F:1393-1396), row ir = the
+ *                              `dslum` of ring ir (telescope.F:1418-1423); rows outside the block = 0
+ *   imcir   (optional) same shape as in rl_render; only the rows of the block are written.
+ * The caller adds the ringsum arrays of all ranks (disjoint blocks: x + 0 is exact) and hands the
+ * total to rl_flux_from_rings, which does the reference's index-ordered sum `slum` and the division
+ * by distance^2 -- the result is bit-identical to rl_render on one GPU. */
+int rl_render_rings(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
+                    int ring_lo, int ring_hi, double *ringsum, double *imcir);
+int rl_flux_from_rings(rl_ctx *ctx, int nl, int nfr, double dist_cm, const double *ringsum,
+                       double *flux);
+
 /* work counters since the last reset: R = ray-channel integrations (charintline calls the
  * reference would make), E = element integrations (integrate_element_linedust calls incl.
  * sub-grid steps), S = ray segments visited. */

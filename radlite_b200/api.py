@@ -33,6 +33,12 @@ def load_library() -> C.CDLL:
         _lib.rl_render_device.restype = C.c_int
         _lib.rl_fetch_flux.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lib.rl_fetch_flux.restype = C.c_int
+        dp = C.POINTER(C.c_double)
+        _lib.rl_render_rings.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                         C.c_int, C.c_int, dp, dp]
+        _lib.rl_render_rings.restype = C.c_int
+        _lib.rl_flux_from_rings.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, dp, dp]
+        _lib.rl_flux_from_rings.restype = C.c_int
         _lib.rl_launch_count.argtypes = [C.c_void_p]
         _lib.rl_launch_count.restype = C.c_longlong
         _lib.rl_total_nodes.argtypes = [C.c_void_p]
@@ -64,6 +70,24 @@ class Renderer(Binding):
         self._check(self.lib.rl_render_device(self.ctx, int(iline0), int(nl), int(nfr),
                                               float(vmax_kms), float(dist_cm), ms))
         return [float(x) for x in ms]
+
+    def render_rings(self, iline0, nl, nfr, vmax_kms, dist_cm, ring_lo, ring_hi, image=None):
+        """Trace only the camera rings ring_lo..ring_hi (0 = central beam): the per-rank piece of a
+        ring-block sharded render.  Returns ringsum[nl, nrr+1, nfr] (rows outside the block are 0);
+        ``image`` (optional, full [nl, nrr+1, nphi, nfr] array) receives the rows of the block."""
+        nrr, _, _ = self.camera_dims()
+        rs = np.zeros((nl, nrr + 1, nfr))
+        self._check(self.lib.rl_render_rings(self.ctx, int(iline0), int(nl), int(nfr), float(vmax_kms),
+                                             float(dist_cm), int(ring_lo), int(ring_hi), _d(rs), _d(image)))
+        return rs
+
+    def flux_from_rings(self, ringsum, dist_cm):
+        """Index-ordered ring sum / distance^2 (telescope.F:1388-1433) of gathered ring sums."""
+        ringsum = np.ascontiguousarray(ringsum, dtype=np.float64)
+        nl, _, nfr = ringsum.shape
+        flux = np.zeros((nl, nfr))
+        self._check(self.lib.rl_flux_from_rings(self.ctx, nl, nfr, float(dist_cm), _d(ringsum), _d(flux)))
+        return flux
 
     def invalidate_geometry(self):
         self.lib.rl_invalidate_geometry.argtypes = [C.c_void_p]

@@ -27,8 +27,8 @@ int tile_smem_limit(int threads);
 int tile_max_lines(int threads);
 void launch_fill(const RenderParams &P, cudaStream_t st);
 void launch_center_replicate(const RenderParams &P, cudaStream_t st);
-void launch_flux(const RenderParams &P, const double *surf, double *ring, double dist2, double *flux,
-                 cudaStream_t st);
+void launch_ringsum(const RenderParams &P, const double *surf, double *ring, cudaStream_t st);
+void launch_flux(int nl, int nrr, int nfr, const double *ring, double dist2, double *flux, cudaStream_t st);
 void launch_cmask(const RenderParams &P, unsigned char *accum, int *out, cudaStream_t st);
 void launch_dfma_peak(double *sink, int iters, int blocks, int threads, cudaStream_t st);
 }  // namespace rl
@@ -600,7 +600,8 @@ static int ensure_geometry(rl_ctx *c) {
 // ---- render -----------------------------------------------------------------------------------
 static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
                        double *flux, double *imcir, int *cmask, double *tau_center, int *maserflag,
-                       double *velo_out, float *kernel_ms, bool device_only) {
+                       double *velo_out, float *kernel_ms, bool device_only, int ring_lo = 0,
+                       int ring_hi = 1 << 30, double *ringsum = nullptr) {
   // telescope.F:366-370, 1511-1515 readiness checks
   if (!c->nr || !c->have_medium || !c->nlines || !(c->have_dust || c->have_line_dust) || !c->cam_set ||
       !c->bc_set)
@@ -608,6 +609,10 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
   if (iline0 < 1 || nl < 1 || iline0 + nl - 1 > c->nlines) return fail(c, 13, "render: line range out of bounds");
   if (nfr < 1) return fail(c, 13, "Number of frequencies for this line is out of range");
   if (nfr == 1) return fail(c, 13, "ERROR: Simple square line profile deactivated");
+  ring_hi = std::min(ring_hi, c->nrr);
+  if (ring_lo < 0 || ring_lo > ring_hi) return fail(c, 13, "render: ring block out of bounds");
+  const bool ring_block = ring_lo > 0 || ring_hi < c->nrr;
+  if (ring_block && cmask) return fail(c, 13, "render: cmask is not available for a ring block");
   if (c->bc_set && c->cfreq_b.empty())
     return fail(c, 1, "ERROR: Cannot use line stellar BC without having read the stellar spectrum.");
   if (c->out_itype == 1) return fail(c, 13, "Outer BC type 1 not allowed for telescope");
@@ -750,7 +755,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     CU(c->d_ncta.ensure((size_t)c->nray + 1));
     CU(c->d_cta_off.ensure((size_t)c->nray + 1));
     CU(c->d_img.ensure((size_t)nb * nrow * nfr));
-    CU(c->d_ring.ensure((size_t)nb * c->nrr * nfr));
+    CU(c->d_ring.ensure((size_t)nb * (c->nrr + 1) * nfr));
     CU(c->d_flux.ensure((size_t)nl * nfr));
     CU(c->d_tau.ensure(nb));
     CU(c->d_maser.ensure(nb));
@@ -804,6 +809,8 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.nfr = nfr;
     P.subgrid = c->subgrid;
     P.nonredundant = c->nonredundant;
+    P.ring_lo = ring_lo;
+    P.ring_hi = ring_hi;
     P.levthres = c->levthres;
     P.aksmax_c = aksmax / 2.99792458e5;
     {
@@ -879,7 +886,8 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     }
     CU(cudaEventRecord(c->ev[3], c->st));
     // ---- flux ----
-    launch_flux(P, c->d_surf.p, c->d_ring.p, dist_cm * dist_cm, c->d_flux.p + (size_t)b0 * nfr, c->st);
+    launch_ringsum(P, c->d_surf.p, c->d_ring.p, c->st);
+    launch_flux(nb, c->nrr, nfr, c->d_ring.p, dist_cm * dist_cm, c->d_flux.p + (size_t)b0 * nfr, c->st);
     c->launches += 2;
     if (want_mask) {
       launch_cmask(P, c->d_cmask_accum.p, c->d_cmask_out.p, c->st);
@@ -889,9 +897,19 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     CU(cudaGetLastError());
     // ---- results back ----
     if (!device_only) {
-      if (imcir)
+      if (imcir && !ring_block)
         CU(cudaMemcpyAsync(imcir + (size_t)b0 * nrow * nfr, c->d_img.p, (size_t)nb * nrow * nfr * sizeof(double),
                            cudaMemcpyDeviceToHost, c->st));
+      if (imcir && ring_block)  // only the rows of this block (the other ranks own the rest of the cube)
+        for (int l = 0; l < nb; l++) {
+          const size_t o = ((size_t)l * nrow + (size_t)ring_lo * c->nphi) * nfr;
+          CU(cudaMemcpyAsync(imcir + (size_t)b0 * nrow * nfr + o, c->d_img.p + o,
+                             (size_t)(ring_hi - ring_lo + 1) * c->nphi * nfr * sizeof(double),
+                             cudaMemcpyDeviceToHost, c->st));
+        }
+      if (ringsum)
+        CU(cudaMemcpyAsync(ringsum + (size_t)b0 * (c->nrr + 1) * nfr, c->d_ring.p,
+                           (size_t)nb * (c->nrr + 1) * nfr * sizeof(double), cudaMemcpyDeviceToHost, c->st));
       if (want_mask)
         CU(cudaMemcpyAsync(cmask + (size_t)b0 * nrow * nfr, c->d_cmask_out.p,
                            (size_t)nb * nrow * nfr * sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -937,6 +955,31 @@ int rl_render_device(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, do
                      float *kernel_ms) {
   return render_impl(c, iline0, nl, nfr, vmax_kms, dist_cm, nullptr, nullptr, nullptr, nullptr, nullptr,
                      nullptr, kernel_ms, true);
+}
+
+int rl_render_rings(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm, int ring_lo,
+                    int ring_hi, double *ringsum, double *imcir) {
+  if (!ringsum) return fail(c, 13, "render_rings: ringsum pointer is required");
+  if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
+  std::vector<double> flux((size_t)std::max(nl, 1) * std::max(nfr, 1));
+  return render_impl(c, iline0, nl, nfr, vmax_kms, dist_cm, flux.data(), imcir, nullptr, nullptr, nullptr,
+                     nullptr, nullptr, false, ring_lo, ring_hi, ringsum);
+}
+
+int rl_flux_from_rings(rl_ctx *c, int nl, int nfr, double dist_cm, const double *ringsum, double *flux) {
+  if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
+  if (nl < 1 || nfr < 1 || !ringsum || !flux) return fail(c, 13, "flux_from_rings: bad arguments");
+  cudaSetDevice(c->device);
+  const size_t n = (size_t)nl * (c->nrr + 1) * nfr;
+  DevBuf<double> d_r, d_f;
+  CU(d_r.upload(ringsum, n, c->st));
+  CU(d_f.ensure((size_t)nl * nfr));
+  launch_flux(nl, c->nrr, nfr, d_r.p, dist_cm * dist_cm, d_f.p, c->st);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(flux, d_f.p, (size_t)nl * nfr * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
 }
 
 int rl_fetch_flux(rl_ctx *c, int nl, int nfr, double *flux) {

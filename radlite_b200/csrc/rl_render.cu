@@ -169,6 +169,16 @@ __global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
   const int ray = blockIdx.x, tid = threadIdx.x;
   const int l = tid;  // the line this thread owns in the second phase
   const long long task = (long long)ray * P.nl + l;
+  {  // ring-block sharding (multi-GPU single-line configs): rays of other ranks carry no items
+    const int ir = ray == 0 ? 0 : 1 + (ray - 1) / P.nphi;
+    if (ir < P.ring_lo || ir > P.ring_hi) {
+      if (l < P.nl) {
+        P.rng[task] = make_int4(1, 0, -1, 3);
+        P.nitems[task] = 0;
+      }
+      return;
+    }
+  }
   if (ray == 0 || !P.nonredundant) {
     if (l < P.nl) {
       P.rng[task] = make_int4(1, P.nfr - 1, -1, ray == 0 ? 2 : 1);
@@ -1177,6 +1187,7 @@ __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ Rende
   const int ray = (int)(task / P.nl), l = (int)(task % P.nl);
   if (ray == 0) return;
   const int4 rg = P.rng[task];
+  if (rg.w == 3) return;  // ring of another rank
   const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
   double *I = P.img + row * P.nfr;
   // continuum known after channel 0 (if out of range) or after the pre-integrated channel c0
@@ -1225,15 +1236,25 @@ __global__ void center_replicate_kernel(RenderParams P) {
   if (P.integ) P.integ[(base + ip) * P.nfr + c] = 0;
 }
 
-// telescope.F:1418-1423: mean over phi of one ring times the ring area, phi in index order
+// telescope.F:1388-1423: per-ring flux contribution.  Row 0 = the central beam (pi ri(1)^2 I_centre,
+// telescope.F:1393-1396); rows 1..nrr = mean over phi of one ring times the ring area, phi in index
+// order.  Rings outside [ring_lo, ring_hi] (another rank's block) give 0.
 __global__ void __launch_bounds__(128) ringsum_kernel(RenderParams P, const double *surf, double *ring) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = (long long)P.nl * P.nrr * P.nfr;
+  const long long n = (long long)P.nl * (P.nrr + 1) * P.nfr;
   if (i >= n) return;
   const int c = (int)(i % P.nfr);
-  const int ir = 1 + (int)((i / P.nfr) % P.nrr);
-  const int l = (int)(i / ((long long)P.nfr * P.nrr));
+  const int ir = (int)((i / P.nfr) % (P.nrr + 1));
+  const int l = (int)(i / ((long long)P.nfr * (P.nrr + 1)));
+  if (ir < P.ring_lo || ir > P.ring_hi) {
+    ring[i] = 0.0;
+    return;
+  }
   const double *I = P.img + ((size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)ir * P.nphi) * P.nfr + c;
+  if (ir == 0) {
+    ring[i] = surf[0] * I[0];
+    return;
+  }
   double dslum = 0.0;
   if (!P.sparse || !P.nonredundant) {
     for (int ip = 0; ip < P.nphi; ip++) dslum = dslum + I[(size_t)ip * P.nfr];
@@ -1253,17 +1274,16 @@ __global__ void __launch_bounds__(128) ringsum_kernel(RenderParams P, const doub
   ring[i] = dslum;
 }
 
-// telescope.F:1388-1433: sum over rings in index order, divide by distance^2
-__global__ void __launch_bounds__(128) flux_kernel(RenderParams P, const double *surf, const double *ring,
-                                                   double dist2, double *flux) {
+// telescope.F:1388-1433: sum of the contributions in index order (centre, rings 1..nrr), divided by
+// distance^2.  ring: [nl][nrr+1][nfr]
+__global__ void __launch_bounds__(128) flux_kernel(int nl, int nrr, int nfr, const double *ring, double dist2,
+                                                   double *flux) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.nl * P.nfr) return;
-  const int c = i % P.nfr, l = i / P.nfr;
+  if (i >= nl * nfr) return;
+  const int c = i % nfr, l = i / nfr;
   double slum = 0.0;
-  const double dslum = surf[0] * P.img[((size_t)l * (size_t)(P.nrr + 1) * P.nphi) * P.nfr + c];
-  slum = slum + dslum;
-  const double *rg = ring + (size_t)l * P.nrr * P.nfr + c;
-  for (int ir = 0; ir < P.nrr; ir++) slum = slum + rg[(size_t)ir * P.nfr];
+  const double *rg = ring + (size_t)l * (nrr + 1) * nfr + c;
+  for (int ir = 0; ir <= nrr; ir++) slum = slum + rg[(size_t)ir * nfr];
   flux[i] = slum / dist2;
 }
 
@@ -1331,7 +1351,7 @@ int tile_max_lines(int threads) {
   return min(kMaxTileLines, (per_buf - 3 * kSlotBytes - (int)sizeof(HotNode)) / (3 * kPairBytes + (int)sizeof(HotLine)));
 }
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
-  center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);
+  if (P.ring_lo <= 0) center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);
   if (!total_ctas) return;
   if (P.tile_threads == 128) tile_kernel<128><<<total_ctas, 128 + kProducerThreads, P.smem_budget, st>>>(P);
   else tile_kernel<64><<<total_ctas, 64 + kProducerThreads, P.smem_budget, st>>>(P);
@@ -1348,14 +1368,15 @@ void launch_fill(const RenderParams &P, cudaStream_t st) {
 }
 void launch_center_replicate(const RenderParams &P, cudaStream_t st) {
   const long long n = (long long)P.nl * (P.nphi - 1) * P.nfr;
-  if (n <= 0) return;
+  if (n <= 0 || P.ring_lo > 0) return;
   center_replicate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P);
 }
-void launch_flux(const RenderParams &P, const double *surf, double *ring, double dist2, double *flux,
-                 cudaStream_t st) {
-  const long long n = (long long)P.nl * P.nrr * P.nfr;
+void launch_ringsum(const RenderParams &P, const double *surf, double *ring, cudaStream_t st) {
+  const long long n = (long long)P.nl * (P.nrr + 1) * P.nfr;
   ringsum_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, surf, ring);
-  flux_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P, surf, ring, dist2, flux);
+}
+void launch_flux(int nl, int nrr, int nfr, const double *ring, double dist2, double *flux, cudaStream_t st) {
+  flux_kernel<<<(nl * nfr + 127) / 128, 128, 0, st>>>(nl, nrr, nfr, ring, dist2, flux);
 }
 void launch_dfma_peak(double *sink, int iters, int blocks, int threads, cudaStream_t st) {
   dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters);

@@ -104,6 +104,7 @@ struct RenderParams {
   int nl;    // lines in this batch
   int nfr;
   int subgrid, nonredundant;
+  int ring_lo, ring_hi;  // camera rings traced by this call (0 = the centre ray, 1..nrr); others are left out
   double levthres;
   double aksmax_c;  // aksmax/2.99792458d5
   double starfract;  // (rstar/rbeam0)^2 for the centre ray

@@ -55,3 +55,50 @@ def golden_cases():
     m.linewidth *= 0.2
     yield "tiny_narrow_subgrid", m
     yield "tiny_cfg4_nlte", synth.config(4, nr=24, nth=10, nphi=6, nrext=-4, nlines=5)
+
+
+class OracleEngine:
+    """The CPU oracle behind the call shapes the sharding layer expects from an engine
+    (``render``, ``camera_dims``, ``render_rings``, ``flux_from_rings``): lets the world_size-2 gloo
+    tests exercise radlite_b200.shard without a GPU.  Ring sums follow telescope.F:1388-1433."""
+
+    def __init__(self, model):
+        from oracle.oracle_py import Oracle
+        self.o = Oracle()
+        self.o.load_model(model)
+        self.m = model
+
+    def camera_dims(self):
+        return self.o.camera_dims()
+
+    def render(self, *a, **kw):
+        return self.o.render(*a, **kw)
+
+    def render_rings(self, iline0, nl, nfr, vmax_kms, dist_cm, ring_lo, ring_hi, image=None):
+        nrr, nphi, _ = self.o.camera_dims()
+        _, ri = self.o.rings()
+        # the oracle always traces the centre ray; rings outside [max(lo,1), hi] are left zero
+        if ring_hi >= 1:
+            self.o.set_ring_sample(max(ring_lo, 1), ring_hi, 1)
+        else:
+            self.o.set_ring_sample(nrr + 1, nrr + 1, 1)
+        img = self.o.render(iline0, nl, nfr, vmax_kms, dist_cm, want_image=True)["image"]
+        self.o.set_ring_sample(0, 0, 1)
+        rs = np.zeros((nl, nrr + 1, nfr))
+        if ring_lo == 0:
+            rs[:, 0] = (3.14159265359 * (ri[1] * ri[1])) * img[:, 0, 0]
+        for ir in range(max(ring_lo, 1), ring_hi + 1):
+            surf = 3.14159265359 * (ri[ir + 1] * ri[ir + 1] - ri[ir] * ri[ir])
+            d = np.zeros((nl, nfr))
+            for ip in range(nphi):
+                d = d + img[:, ir, ip]
+            rs[:, ir] = d / (1.0 * nphi) * surf
+        if image is not None:
+            image[:, ring_lo:ring_hi + 1] = img[:, ring_lo:ring_hi + 1]
+        return rs
+
+    def flux_from_rings(self, ringsum, dist_cm):
+        s = np.zeros((ringsum.shape[0], ringsum.shape[2]))
+        for ir in range(ringsum.shape[1]):
+            s = s + ringsum[:, ir]
+        return s / (dist_cm * dist_cm)

@@ -166,6 +166,32 @@ def test_spectrum_only_equals_cube_mode(renderer_cls):
         assert np.array_equal(a["maserflag"], b["maserflag"])
 
 
+def test_ring_block_sharding_is_bit_identical(renderer_cls):
+    """rl_render_rings over disjoint ring blocks + rl_flux_from_rings == rl_render, bit for bit
+    (the multi-GPU path of single-line configs, run here as consecutive blocks on one GPU)."""
+    from radlite_b200 import shard
+    for m in (tiny(1), tiny(2, nlines=3), clone(tiny(1), nonredundant=0)):
+        g = renderer_cls(0)
+        g.load_model(m)
+        full = g.render(1, m.nlines, m.nfr, m.passband, synth.PARSEC, want_image=True)
+        nrr, nphi, _ = g.camera_dims()
+        for world in (1, 2, 3):
+            rs = np.zeros((m.nlines, nrr + 1, m.nfr))
+            cube = np.zeros((m.nlines, nrr + 1, nphi, m.nfr))
+            for lo, hi in shard.split_rings(nrr, world):
+                part = g.render_rings(1, m.nlines, m.nfr, m.passband, synth.PARSEC, lo, hi, image=cube)
+                assert not np.delete(part, np.s_[lo:hi + 1], axis=1).any()
+                rs = rs + part
+            assert np.array_equal(g.flux_from_rings(rs, synth.PARSEC), full["flux"])
+            assert np.array_equal(cube, full["image"])
+        # spectrum-only (sparse) ring blocks as well
+        rs = sum(g.render_rings(1, m.nlines, m.nfr, m.passband, synth.PARSEC, lo, hi)
+                 for lo, hi in shard.split_rings(nrr, 2))
+        assert np.array_equal(g.flux_from_rings(rs, synth.PARSEC), full["flux"])
+        with pytest.raises(RadliteError):
+            g.render_rings(1, 1, m.nfr, m.passband, synth.PARSEC, 5, 4)
+
+
 def test_error_codes_match_reference_stops(renderer_cls):
     m = tiny()
     g = renderer_cls(0)
