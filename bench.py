@@ -279,8 +279,18 @@ def run_gpu(args):
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture
+        traffic, traffic_src = None, None
+        try:
+            import glob
+            tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+            if tfiles and nl == 100:
+                tj = json.load(open(tfiles[-1]))
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], os.path.relpath(tfiles[-1], ROOT)
+        except (OSError, KeyError, ValueError):
+            pass
         value = R_tot / dev_s_max
-        # dominant kernel: integrate_kernel, one launch per step (100 lines fit one batch)
+        # dominant kernel: tile_kernel, one launch per step (100 lines fit one batch)
         n_launch = args.steps * max(1, -(-nl // max(1, nl)))
         E_rank = cnt["E"]
         achieved_tf = E_rank * FLOP_PER_ELEMENT / (ms[2] * 1e-3) / 1e12
@@ -316,11 +326,14 @@ def run_gpu(args):
             "strong": {"what": "wall time of ONE %d-line spectrum block-partitioned over %d GPU(s) incl. "
                                "final gather" % (nl, world), "ms": 1e3 * strong_max / args.steps},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak, "traffic": None,
-                         "kernel": "integrate_kernel",
-                         "how": "E element integrations x 64 FP64 flop (exp excluded) / CUDA-event time of "
-                                "the integrate kernel; peak = DFMA microbenchmark measured in this run "
-                                "(MEASURED_PEAKS.json has no FP64 entry)",
+                         "frac": achieved_tf / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "traffic_source": traffic_src,
+                         "kernel": "tile_kernel<128> (ray x (line, channel) tile formal solution)",
+                         "how": "E element integrations x 64 FP64 flop (SURVEY.md 8d, exp excluded) / CUDA-event "
+                                "time of the integrate phase (tile_kernel + centre ray) on the library's stream; "
+                                "peak = DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no "
+                                "FP64 entry); the path is FP64 arithmetic on L2-resident data, so the hbm "
+                                "figure below is reported for completeness only",
                          "achieved_exp22": E_rank * (FLOP_PER_ELEMENT + 44.0) / (ms[2] * 1e-3) / 1e12,
                          "hbm": {"achieved": alg_bytes * args.steps / (ms[2] * 1e-3) / 1e9, "peak": hbm_peak,
                                  "unit": "GB/s", "frac": alg_bytes * args.steps / (ms[2] * 1e-3) / 1e9 / hbm_peak,

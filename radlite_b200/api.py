@@ -14,7 +14,8 @@ import numpy as np
 from ._binding import Binding, RadliteError, _d, _i
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libradlite_b200.so")
+# RADLITE_B200_LIB selects a tuning variant built by `make variant` (development only)
+LIB_PATH = os.environ.get("RADLITE_B200_LIB") or os.path.join(_HERE, "libradlite_b200.so")
 _lib = None
 
 

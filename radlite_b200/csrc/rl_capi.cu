@@ -646,7 +646,8 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
   lb = std::max(1, std::min(lb, nl));
   // tile_kernel: 128-thread blocks when a ray carries enough (line, channel) items, else 64; a tile
   // must hold two slots of all its lines in shared memory twice (double buffer)
-  const int tile_threads = (lb >= 16) ? 128 : 64;
+  int tile_threads = (lb >= 16) ? 128 : 64;
+  if (const char *e = getenv("RL_TILE_THREADS")) tile_threads = atoi(e) == 64 ? 64 : 128;  // tuning experiments
   // (the lines a tile spans are bounded by plan_kernel, not by the batch size)
   lb = std::min(lb, kSpanThreads);  // span_kernel: one thread and one mask bit per line
   if (want_mask) {
@@ -688,7 +689,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
       L.c_src = 5.27296241956e-28 * L.nu0 * L.aud;    // line.F:4571
       L.c_alp = 5.27296241956e-28 * L.nu0;            // line.F:4584
       L.inv_nu0 = 1.0 / L.nu0;
-      L.kia = 19.217958540583197 / L.k_aa;  // sqrt(256/ln 2) / k_aa
+      L.kia = kTabSqrtScale / L.k_aa;  // sqrt(kTabN/ln 2) / k_aa
       if (c->out_itype == 2) {  // telescope.F:3996-4000
         const double f = c->linefreq[il];
         L.i_outer = 1.47455253991e-47 * (f * f * f) / (std::exp(4.7991598e-11 * f / kTempCmb) - 1.0);

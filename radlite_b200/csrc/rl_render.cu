@@ -270,11 +270,7 @@ __global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
   P.nitems[task] = (unsigned)n;
 }
 
-// number of channels the reference integrates for a task and the j-th of them
-__device__ __forceinline__ int task_nchan(const RenderParams &P, const int4 rg) {
-  if (rg.w == 2 || !P.nonredundant) return P.nfr;
-  return 1 + ((rg.y >= rg.x) ? (rg.y - rg.x + 1) : 0) + (rg.z >= 0 ? 1 : 0);
-}
+// the j-th channel the reference integrates for a task (rng = {lo, hi, c0, kind})
 __device__ __forceinline__ int task_chan(const RenderParams &P, const int4 rg, int j, bool &masked) {
   if (rg.w == 2) { masked = false; return j; }  // centre ray: the reference never sets its mask
   if (!P.nonredundant) { masked = (j == 0); return j; }  // telescope.F:548 only
@@ -444,37 +440,55 @@ __device__ __forceinline__ long long img_row(const RenderParams &P, int ray) {
 // ------------------------------------------------------------------------------------------
 // tile_kernel: the formal solution for one ray x a tile of (line, channel) items.
 //
-// One thread block owns one camera ray and a tile of consecutive entries of the ray's item list
-// (all channels the reference integrates, lines in index order: "ray x line tile"), one item per
-// thread.  The ray's nodes
-// are processed in chunks through a double-buffered shared-memory stage: while the block integrates
-// chunk c, the same threads gather and interpolate the cell values of chunk c+1 and precompute, per
-// (node, line of the tile), every channel-independent constant of the line profile -- so that work
-// is done once per ray, line and node instead of once per channel, and its memory latency hides
-// behind the arithmetic of the current chunk.  One barrier per chunk.
+// One thread block owns one camera ray and a tile of consecutive entries of the ray's item list (all
+// channels the reference integrates, lines in index order: "ray x line tile"), one item per consumer
+// thread.  A producer warp walks the ray's nodes in chunks: it gathers and interpolates the cell values
+// of every (node, line of the tile) pair and precomputes every channel-independent constant of the line
+// profile -- that work is done once per ray, line and node instead of once per channel -- and stages
+// the chunk in a ring of kTileBufs shared-memory buffers.  The consumer warps never touch global
+// memory inside the ray loop.  Hand-over by mbarriers: full[b] (producer -> consumers) and empty[b]
+// (each consumer warp -> producer), so consumer warps are not coupled to each other.
 //
-// All threads of a block walk the same ray: no trip-count divergence.  The integration step is
-// three-way, decided by a warp vote (the same case split as transfer.F:1517,1542):
-//   * every lane has dtau <= 1e-9 (about 2/3 of all steps in disk atmospheres): I <- I (1-dtau) + theomax
+// All threads of a block walk the same ray: no trip-count divergence.  Segments are integrated in
+// groups of RL_JAM whose dependency chains interleave (jam_steps); the case split of transfer.F:1517,
+// 1542 is a warp vote per group:
+//   * every lane has dtau <= 1e-9 on every segment of the group (about 2/3 of all steps in disk
+//     atmospheres): I <- I (1-dtau) + theomax
 //   * otherwise the full qdr_src_2 step with e^-dtau and the source-function ratios
 //   * nodes flagged by the geometry (first segment, inner hole / star mixing, 6q > 1 sub-grid
-//     candidates) take a separate reference-ordered path.
+//     candidates) take a separate reference-ordered path (slow_step).
 //
 // Arithmetic notes (all deviations from the reference are << the 1e-6 tolerance):
-//   exp(x), x <= 0: n = round(x 256/ln2), exp = 2^(n>>8) T1[n&255] P(r), with one 256-entry
-//   shared-memory table and |r| <= ln2/512; P = cubic for the line profile (< 1.5e-13), quartic for
-//   exp(-dtau) (< 4e-17).  The Gaussian argument is carried pre-scaled so that n and r fall out of
-//   two FMAs.  Profile values below exp(-345) are flushed to 0.  Divisions: hardware reciprocal seed
-//   + two Newton steps (< 2e-11).
+//   exp(x), x <= 0: n = round(x kTabN/ln2), exp = 2^(n>>kTabBits) T1[n & (kTabN-1)] P(r), with one small
+//   shared-memory table and |r| <= ln2/(2 kTabN); P = degree kDegGauss for the line profile (< 1.5e-13),
+//   kDegTau for exp(-dtau) (< 2e-18).  The Gaussian argument is carried pre-scaled so that n and r fall
+//   out of two FMAs.  Profile values below exp(-345) are flushed to 0.  Divisions: hardware reciprocal
+//   seed + two Newton steps (< 2e-11).
 // ------------------------------------------------------------------------------------------
 constexpr double kExpMagic = 6755399441055744.0;       // 1.5 * 2^52
-constexpr double kLog2eS = 369.3299304675746;          // 256 / ln 2
-constexpr double kLn2S = 0.0027076061740622863;        // L = ln 2 / 256
-constexpr double kLn2S2 = 3.6655655969101062e-06;      // L^2 / 2
-constexpr double kLn2S3 = 3.3083026805413713e-09;      // L^3 / 6
-constexpr double kLn2S4 = 2.239395190875157e-12;       // L^4 / 24
-constexpr double kCnorm = 0.029357740275512044;        // 0.56419583546 / sqrt(256 / ln 2)
-constexpr unsigned kHiUmax = 0x40764f52u;              // hi word of sqrt(345 * 256/ln 2): exp(-345) ~ 1e-150
+constexpr double kLn2 = 0.6931471805599453;
+constexpr double kLog2eS = (double)kTabN / kLn2;       // kTabN / ln 2
+constexpr double kLn2S = kLn2 / (double)kTabN;         // L = ln 2 / kTabN
+constexpr double kCnorm = 0.56419583546 / kTabSqrtScale;
+// Taylor coefficients L^k / k! of exp(L rp), |rp| <= 1/2
+template <int K>
+__host__ __device__ constexpr double exp_coef() {
+  return exp_coef<K - 1>() * kLn2S / (double)K;
+}
+template <>
+__host__ __device__ constexpr double exp_coef<0>() {
+  return 1.0;
+}
+template <int K>
+struct Horner {
+  static __device__ __forceinline__ double run(double p, double rp) {
+    return Horner<K - 1>::run(fma(p, rp, exp_coef<K>()), rp);
+  }
+};
+template <>
+struct Horner<-1> {
+  static __device__ __forceinline__ double run(double p, double) { return p; }
+};
 constexpr unsigned kHiTauMax = 0x40859000u;            // hi word of 690.0
 constexpr double kAlpTiny = 1.0e-280;                  // alpha <= this is treated like alpha <= 0
 
@@ -527,28 +541,25 @@ __device__ __forceinline__ double div_fast(double n, double x) {
   return fma(q, e, q);
 }
 
-// 2^(n / 256) e^r, r = rp ln2/256, |rp| <= 1/2: one 256-entry table of 2^(j/256) (a single 8-byte
-// shared-memory read per exp: the LSU data pipe, not the FP64 pipe, was the limiter with larger
-// tables) and a short polynomial.  DEG = 3: relative error r^4/24 < 1.5e-13 (the line profile);
-// DEG = 4: r^5/120 < 4e-17 (exp(-dtau) feeds the cancelling differences e0 = 1 - xp, e1 = dtau - e0
-// of transfer.F:1519-1520, whose error is the absolute error of xp).  T1 = shared-window address.
+// 2^(n / kTabN) e^r, r = rp ln2/kTabN, |rp| <= 1/2: one table read of 2^(j/kTabN) (a single 8-byte
+// shared-memory read per exp: the LSU data pipe, not the FP64 pipe, is the scarce resource) and a short
+// polynomial of degree DEG (relative error r^(DEG+1)/(DEG+1)!).  exp(-dtau) needs the longer one: it
+// feeds the cancelling differences e0 = 1 - xp, e1 = dtau - e0 of transfer.F:1519-1520, whose error is
+// the absolute error of xp.  T1 = shared-window address of the table.
 template <int DEG>
 __device__ __forceinline__ double exp_tab(double t, double rp, uint32_t T1) {
   const int n = __double2loint(t);
-  const double v = lds_f64(T1 + ((n << 3) & 0x7f8));
-  double p = (DEG == 4) ? fma(rp, kLn2S4, kLn2S3) : kLn2S3;
-  p = fma(p, rp, kLn2S2);
-  p = fma(p, rp, kLn2S);
-  p = fma(p, rp, 1.0);
-  const int hi = __double2hiint(v) + ((n >> 8) << 20);
+  const double v = lds_f64(T1 + ((n & (kTabN - 1)) << 3));
+  const double p = Horner<DEG - 1>::run(exp_coef<DEG>(), rp);
+  const int hi = __double2hiint(v) + ((n >> kTabBits) << 20);
   return __hiloint2double(hi, __double2loint(v)) * p;
 }
-// exp(-u^2 ln2/256) for the pre-scaled argument u; exactly 0 beyond exp(-345)
+// exp(-u^2 ln2/kTabN) for the pre-scaled argument u; exactly 0 beyond exp(-345)
 __device__ __forceinline__ double gauss_tab(double u, uint32_t T1, uint32_t T2) {
   const double t = fma(-u, u, kExpMagic);
   const double fn = t - kExpMagic;
   const double rp = fma(-u, u, -fn);
-  const double e = exp_tab<3>(t, rp, T1);
+  const double e = exp_tab<kDegGauss>(t, rp, T1);
   const bool far = ((unsigned)__double2hiint(u) & 0x7fffffffu) > kHiUmax;
   return far ? 0.0 : e;
 }
@@ -559,15 +570,15 @@ __device__ __forceinline__ double expneg_tab(double d, uint32_t T1, uint32_t T2)
   const double t = fma(dc, -kLog2eS, kExpMagic);
   const double fn = t - kExpMagic;
   const double rp = fma(dc, -kLog2eS, -fn);
-  return exp_tab<4>(t, rp, T1);
+  return exp_tab<kDegTau>(t, rp, T1);
 }
 
-// the qdr_src_2 step (transfer.F:1498-1571) with all case selections branch free; r0 = src0/alp0
-// comes in, r1 = src1/alp1 goes out
-__device__ __forceinline__ void full_step(double &inten, double alp0, double r0, double src1, double alp1,
-                                          double &r1, double dtau, double theomax, uint32_t T1, uint32_t T2) {
+// the qdr_src_2 step (transfer.F:1498-1571) with all case selections branch free: r0 = src0/alp0 comes
+// in, r1 = src1/alp1 goes out; the step itself is I <- I x + qv
+__device__ __forceinline__ void step_coeffs(double alp0, double r0, double src1, double alp1, double &r1,
+                                            double dtau, double theomax, uint32_t T1, double &x, double &qv) {
   r1 = div_fast(src1, alp1);
-  const double xpe = expneg_tab(dtau, T1, T2);
+  const double xpe = expneg_tab(dtau, T1, 0);
   const double e0 = 1.0 - xpe;
   const double ee1 = dtau - e0;
   const double bt = div_fast(ee1, dtau);
@@ -575,12 +586,18 @@ __device__ __forceinline__ void full_step(double &inten, double alp0, double r0,
   const bool thick = dtau > 1.e-6;
   const double b = thick ? bt : hb;
   const double a = thick ? (e0 - bt) : hb;
-  const double x = thick ? xpe : (1.0 - dtau);
+  x = thick ? xpe : (1.0 - dtau);
   const bool p0 = alp0 > kAlpTiny, p1 = alp1 > kAlpTiny;
   const double s_a = p0 ? r0 : (p1 ? r1 : 0.0);
   const double s_b = p1 ? r1 : (p0 ? r0 : 0.0);
-  double qv = fma(a, s_a, b * s_b);
+  qv = fma(a, s_a, b * s_b);
   qv = (dtau > (double)1e-9f) ? fmin(qv, theomax) : theomax;
+}
+
+__device__ __forceinline__ void full_step(double &inten, double alp0, double r0, double src1, double alp1,
+                                          double &r1, double dtau, double theomax, uint32_t T1, uint32_t) {
+  double x, qv;
+  step_coeffs(alp0, r0, src1, alp1, r1, dtau, theomax, T1, x, qv);
   inten = fma(inten, x, qv);
 }
 
@@ -630,7 +647,7 @@ __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch,
 
 // per-block tables and per-item metadata of tile_kernel (file scope: the out-of-line slow path uses
 // them too)
-__shared__ double s_T1[256];         // 2^(j/256)
+__shared__ double s_T1[kTabN];       // 2^(j/kTabN)
 __shared__ int2 s_meta[128];      // {line slot, channel | cmask bit} of the thread's item
 __shared__ unsigned s_flags[128]; // maser | extra elements << 8 of the thread's item
 __shared__ double s_dnu[128];     // line_dnu of the thread's item
@@ -707,16 +724,38 @@ __device__ __noinline__ unsigned slow_step(double *st, TileBuf B, int nlc, int s
   st[3] = r0;
   return ret;
 }
-// named barriers of tile_kernel (0 is __syncthreads): "buffer b holds a staged chunk" and "buffer b
-// has been consumed"
+// named barrier (0 is __syncthreads): only used among the producer warps when there are several
 __device__ __forceinline__ void bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-__device__ __forceinline__ void bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+// mbarrier hand-over of the staged chunks: full[b] is signalled by the producer warp(s),
+// empty[b] by every consumer warp on its own, so the consumer warps of a block are NOT coupled to each
+// other -- each runs ahead as far as the ring allows.
+__shared__ unsigned long long s_mbar[8];  // full[0..kTileBufs), empty[0..kTileBufs)
+__device__ __forceinline__ void mbar_init(uint32_t a, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n}" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nRL_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RL_MBAR_DONE;\nbra RL_MBAR_WAIT;\nRL_MBAR_DONE:\n}" ::"r"(a), "r"(parity)
+      : "memory");
 }
 constexpr int kTileBufs = 3;        // staged chunks in flight
-constexpr int kProducerThreads = 32;  // one staging warp per block
+#ifndef RL_PRODUCER_WARPS
+#define RL_PRODUCER_WARPS 1
+#endif
+#ifndef RL_PAIRS_IN_FLIGHT
+#define RL_PAIRS_IN_FLIGHT 2
+#endif
+constexpr int kProducerWarps = RL_PRODUCER_WARPS;      // staging warps per block
+constexpr int kProducerThreads = 32 * kProducerWarps;
+constexpr int kPairsInFlight = RL_PAIRS_IN_FLIGHT;     // (node, line) pairs a producer lane gathers at a time
+constexpr int kBarProducers = 15;                      // named barrier among the producer warps
 
 // ---- producer side of tile_kernel -----------------------------------------------------------
 // per-tile line constants and the node records of the chunk being staged / the next one
@@ -802,9 +841,10 @@ __device__ __forceinline__ void pair_store(const TileBuf &B, int p, int slot, in
 // shared memory; every lane then handles four (node, line) pairs at a time with all their gathers
 // in flight together.
 __device__ __noinline__ void producer_loop(const RenderParams &P, uint32_t smem0, int bufbytes, int nch,
-                                           int nlc, int l0, long long n0, int N, int nchunks, int lane,
+                                           int nlc, int l0, long long n0, int N, int nchunks, int plane,
                                            int nall) {
-  for (int m = lane; m < nlc; m += 32) {
+  constexpr int NP = kProducerThreads;
+  for (int m = plane; m < nlc; m += NP) {
     const LineDev *Lm = P.lines + (l0 + m);
     LineC lc;
     lc.c_src = __ldg(&Lm->c_src); lc.c_alp = __ldg(&Lm->c_alp); lc.bud = __ldg(&Lm->bud);
@@ -814,24 +854,31 @@ __device__ __noinline__ void producer_loop(const RenderParams &P, uint32_t smem0
   const NodeRec *rec = P.nodes.rec + n0;
   // node records travel global -> shared without passing through registers (cp.async, 4 x 16 B)
   auto fetch_nodes = [&](int buf, int first, int count) {
-    if (lane < count) {
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_nodes[buf][lane]);
-      const char *src = reinterpret_cast<const char *>(rec + first + lane);
+    if (plane < count) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_nodes[buf][plane]);
+      const char *src = reinterpret_cast<const char *>(rec + first + plane);
 #pragma unroll
       for (int k = 0; k < 4; k++)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * k), "l"(src + 16 * k) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  auto producers_sync = [&]() {
+    if (kProducerWarps == 1) __syncwarp();
+    else bar_sync(kBarProducers, NP);
+  };
+  // q / nlc by multiplication: exact for q < 2^11, nlc <= 64 (q (M nlc - 2^20) < 2^17 < 2^20)
+  const uint32_t Mdiv = ((1u << 20) + (uint32_t)nlc - 1u) / (uint32_t)nlc;
   fetch_nodes(0, 0, min(nch, N - 1) + 1);
   for (int c = 0, b = 0; c < nchunks; c++, b = (b + 1 == kTileBufs) ? 0 : b + 1) {
     const int c0 = 1 + c * nch, cnt = min(nch, N - c0);
     // this chunk's node records have landed; the next chunk's go in flight while this one is staged
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
+    producers_sync();
     const int c0n = c0 + nch;
     if (c + 1 < nchunks) fetch_nodes((c + 1) & 1, c0n - 1, min(nch, N - c0n) + 1);
-    if (c >= kTileBufs) bar_sync(1 + kTileBufs + b, nall);  // empty[b]
+    if (c >= kTileBufs)  // empty[b]: the consumers are done with the chunk staged here kTileBufs chunks ago
+      mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar[kTileBufs + b]), (uint32_t)((c / kTileBufs - 1) & 1));
     TileBuf B;
     B.hn = smem0 + (uint32_t)(b * bufbytes);
     B.hl = B.hn + (uint32_t)((nch + 2) * sizeof(HotNode));
@@ -839,113 +886,131 @@ __device__ __noinline__ void producer_loop(const RenderParams &P, uint32_t smem0
     B.cl = B.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
     const NodeRec *cn = s_nodes[c & 1];
     const int npair = (cnt + 1) * nlc;
-    // four pairs per lane and round, all their gathers in flight together; consecutive lanes take
-    // consecutive lines of one node: with the cell-major layout their records are contiguous
+    // kPairsInFlight pairs per lane and round, all their gathers in flight together; consecutive
+    // lanes take consecutive lines of one node: with the cell-major layout their records are contiguous
     const size_t nl = (size_t)P.nl;
     const double4 *cell0 = P.cellL + l0;
-    for (int p = lane; p < npair; p += 4 * 32) {
-      int slot[4], m[4];
-      bool has[4];
-      PairLoads L[4];
+    for (int p = plane; p < npair; p += kPairsInFlight * NP) {
+      int slot[kPairsInFlight], m[kPairsInFlight];
+      bool has[kPairsInFlight];
+      PairLoads L[kPairsInFlight];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int q = p + 32 * k;
+      for (int k = 0; k < kPairsInFlight; k++) {
+        const int q = p + NP * k;
         has[k] = q < npair;
-        slot[k] = has[k] ? q / nlc : 0;
+        slot[k] = has[k] ? (int)(((uint32_t)q * Mdiv) >> 20) : 0;
         m[k] = has[k] ? q - slot[k] * nlc : 0;
         L[k] = pair_issue(cell0 + m[k], nl, cn + slot[k]);
       }
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < kPairsInFlight; k++) {
         if (has[k])
-          pair_store(B, p + 32 * k, slot[k], m[k], c0 - 1 + slot[k], cn,
+          pair_store(B, p + NP * k, slot[k], m[k], c0 - 1 + slot[k], cn,
                      pair_interp(L[k], cell0 + m[k], nl, cn + slot[k]), P.subgrid);
       }
     }
     __threadfence_block();
     __syncwarp();
-    bar_arrive(1 + b, nall);  // full[b]
+    if ((plane & 31) == 0) mbar_arrive((uint32_t)__cvta_generic_to_shared(&s_mbar[b]));  // full[b]
   }
 }
 
-// what the profile evaluation makes of one staged slot for one item (line.F:4554-4597 at the end
-// point of the segment: profile, line + dust source and opacity)
-struct PreSlot {
-  double src1, alp1, alpl1, hds;
-  uint32_t fl;
-  int k1hi;  // high word of K1: its sign flags inverted populations
-};
-__device__ __forceinline__ PreSlot pre_slot(uint32_t an, uint32_t ah, double dnu, uint32_t T1, uint32_t T2) {
-  PreSlot g;
-  unsigned long long fw;
-  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(g.hds), "=l"(fw) : "r"(an));
-  g.fl = (uint32_t)fw;
-  const double2 iv = lds_f64x2(ah + 32), ak = lds_f64x2(ah + 16), sa = lds_f64x2(ah);
-  const double u = fma(dnu, iv.x, -iv.y);
-  const double e = gauss_tab(u, T1, T2);
-  g.alpl1 = ak.y * e;
-  g.src1 = fma(ak.x, e, sa.x);
-  g.alp1 = sa.y + g.alpl1;
-  g.k1hi = __double2hiint(ak.y);
-  return g;
+// ---- consumer side: the segments of one staged chunk ------------------------------------------------
+// The only true recurrence along the ray is I <- I x + q; the profile, exp(-dtau) and the source-function
+// weights of a segment depend on staged node data alone.  NS consecutive segments are therefore
+// evaluated in ONE basic block (their dependency chains interleave: the warp's instruction-level
+// parallelism is what hides the FP64 latency at 4-5 resident warps per scheduler), then chained into
+// the intensity with NS fused multiply-adds.  The qdr_src_2 case split is voted once per group.
+template <int NS>
+__device__ __forceinline__ void jam_steps(uint32_t an, uint32_t ah, uint32_t stride, double dnu, Item &it,
+                                          int &r0ok, uint32_t T1) {
+  double hds[NS], src1[NS], alp1[NS], alpl1[NS];
+  int k1hi[NS];
+#pragma unroll
+  for (int k = 0; k < NS; k++) {
+    hds[k] = lds_f64(an + (uint32_t)k * (uint32_t)sizeof(HotNode));
+    const uint32_t a = ah + (uint32_t)k * stride;
+    const double2 iv = lds_f64x2(a + 32), ak = lds_f64x2(a + 16), sa = lds_f64x2(a);
+    const double u = fma(dnu, iv.x, -iv.y);
+    const double e = gauss_tab(u, T1, 0);
+    alpl1[k] = ak.y * e;
+    src1[k] = fma(ak.x, e, sa.x);
+    alp1[k] = sa.y + alpl1[k];
+    k1hi[k] = __double2hiint(ak.y);
+  }
+  double dtau[NS], theo[NS];
+  bool work = false;
+  int anyk1 = 0;
+#pragma unroll
+  for (int k = 0; k < NS; k++) {
+    const double a0 = k ? alp1[k - 1] : it.alp0, s0 = k ? src1[k - 1] : it.src0;
+    dtau[k] = hds[k] * (a0 + alp1[k]);
+    theo[k] = hds[k] * (s0 + src1[k]);
+    work = work || (dtau[k] > (double)1e-9f);
+    anyk1 |= k1hi[k];
+  }
+  work = work || (anyk1 < 0);  // inverted populations force the full path, which carries the maser test
+  if (!__any_sync(0xffffffffu, work)) {
+    // transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau
+#pragma unroll
+    for (int k = 0; k < NS; k++) it.inten = fma(it.inten, 1.0 - dtau[k], theo[k]);
+    r0ok = 0;
+  } else {
+    double r = r0ok ? it.r0 : div_fast(it.src0, it.alp0);
+    double x[NS], q[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      const double a0 = k ? alp1[k - 1] : it.alp0;
+      double rn;
+      step_coeffs(a0, r, src1[k], alp1[k], rn, dtau[k], theo[k], T1, x[k], q[k]);
+      r = rn;
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) it.inten = fma(it.inten, x[k], q[k]);
+    if (__any_sync(0xffffffffu, anyk1 < 0)) {  // telescope.F:4295
+      bool ms = false;
+#pragma unroll
+      for (int k = 0; k < NS; k++) ms = ms || (alpl1[k] * (hds[k] + hds[k]) < (double)(-0.01f));
+      if (ms) s_flags[threadIdx.x] |= 1u;
+    }
+    it.r0 = r;
+    r0ok = 1;
+  }
+  it.src0 = src1[NS - 1];
+  it.alp0 = alp1[NS - 1];
 }
 
-// the segments of one staged chunk for the thread's item, software pipelined: the profile of slot
-// s+1 (which does not depend on the carried state) is evaluated in the same basic block as the
-// optical-depth test of slot s, so its shared-memory and table latencies overlap.  The slot after
-// the chunk's last one is a phantom (stale data, read but never used).  Flagged nodes (rare) are
-// handled by an out-of-line call between runs of the register-resident loop; everything but the
-// item state is re-materialised after such a call (manual live-range splitting).
+#ifndef RL_JAM
+#define RL_JAM 3
+#endif
 __device__ __forceinline__ void integrate_chunk(const RenderParams &P, const TileBuf B, int nlc, int cnt,
-                                                Item &it, int l0, int &r0ok) {
-  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1), T2 = 0;
+                                                    Item &it, int l0, int &r0ok) {
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
+  const uint32_t stride = (uint32_t)nlc * (uint32_t)sizeof(HotLine);
+  const double dnu = s_dnu[threadIdx.x];
+  const uint32_t ah0 = B.hl + (uint32_t)(s_meta[threadIdx.x].x - l0) * (uint32_t)sizeof(HotLine);
   int slot = 1;
   while (slot <= cnt) {
-    const uint32_t stride = (uint32_t)nlc * (uint32_t)sizeof(HotLine);
-    const double dnu = s_dnu[threadIdx.x];
-    uint32_t an = B.hn + (uint32_t)slot * (uint32_t)sizeof(HotNode);
-    uint32_t ah = B.hl + (uint32_t)slot * stride +
-                  (uint32_t)(s_meta[threadIdx.x].x - l0) * (uint32_t)sizeof(HotLine);
-    PreSlot pa = pre_slot(an, ah, dnu, T1, T2), pb;
-    // one pipeline beat: evaluate the profile of slot+1 into `pout`, advance the intensity over
-    // `slot` with `pin`.  Unrolled twice with the roles of the A and B registers swapped.
-#define RL_BEAT(pin, pout)                                                                         \
-  {                                                                                                \
-    an += (uint32_t)sizeof(HotNode);                                                               \
-    ah += stride;                                                                                  \
-    /* transfer.F:1498-1571 for `slot` */                                                          \
-    const double dtau = pin.hds * (it.alp0 + pin.alp1);                                            \
-    const double theo = pin.hds * (it.src0 + pin.src1);                                            \
-    /* inverted populations (K1 < 0) force the full path, which carries the maser test */          \
-    const bool work = (dtau > (double)1e-9f) || (pin.k1hi < 0);                                    \
-    pout = pre_slot(an, ah, dnu, T1, T2);                                                          \
-    if (pin.fl) break; /* block-uniform: this node takes the out-of-line path */                   \
-    if (!__any_sync(0xffffffffu, work)) {                                                          \
-      /* transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau */                                  \
-      it.inten = fma(it.inten, 1.0 - dtau, theo);                                                  \
-      r0ok = 0;                                                                                    \
-    } else {                                                                                       \
-      if (!r0ok) it.r0 = div_fast(it.src0, it.alp0);                                               \
-      double r1;                                                                                   \
-      full_step(it.inten, it.alp0, it.r0, pin.src1, pin.alp1, r1, dtau, theo, T1, T2);             \
-      it.r0 = r1;                                                                                  \
-      if (__any_sync(0xffffffffu, pin.k1hi < 0)) { /* telescope.F:4295 */                          \
-        if (pin.alpl1 * (pin.hds + pin.hds) < (double)(-0.01f)) s_flags[threadIdx.x] |= 1u;        \
-      }                                                                                            \
-      r0ok = 1;                                                                                    \
-    }                                                                                              \
-    it.src0 = pin.src1;                                                                            \
-    it.alp0 = pin.alp1;                                                                            \
-    slot++;                                                                                        \
-    if (slot > cnt) break;                                                                         \
-  }
-    for (;;) {
-      RL_BEAT(pa, pb)
-      RL_BEAT(pb, pa)
+    const uint32_t an = B.hn + (uint32_t)slot * (uint32_t)sizeof(HotNode);
+    const uint32_t ah = ah0 + (uint32_t)slot * stride;
+    // flags of the next RL_JAM slots (block-uniform); slots past the chunk count as flagged
+    uint32_t fl[RL_JAM];
+#pragma unroll
+    for (int k = 0; k < RL_JAM; k++)
+      fl[k] = (slot + k <= cnt) ? smem_ptr<HotNode>(B.hn)[slot + k].flags : 1u;
+    int n = 0;  // number of leading unflagged slots
+#pragma unroll
+    for (int k = 0; k < RL_JAM; k++) {
+      if (fl[k]) break;
+      n = k + 1;
     }
-#undef RL_BEAT
-    if (slot > cnt) break;
-    {
+    if (n == RL_JAM) {
+      jam_steps<RL_JAM>(an, ah, stride, dnu, it, r0ok, T1);
+      slot += RL_JAM;
+    } else if (n >= 1) {
+      jam_steps<1>(an, ah, stride, dnu, it, r0ok, T1);
+      slot += 1;
+    } else {
       const int2 mt = s_meta[threadIdx.x];
       double st[4] = {it.inten, it.src0, it.alp0, it.r0};
       const unsigned f = slow_step(st, B, nlc, slot, mt.x, mt.x - l0, mt.y & 0x3fffffff, s_dnu[threadIdx.x],
@@ -966,13 +1031,19 @@ __device__ __forceinline__ void integrate_chunk(const RenderParams &P, const Til
 // kTileBufs shared-memory buffers; the consumers never touch global memory inside the ray loop (the
 // flagged-node path excepted).  Hand-over by named barriers: full[b] (producer arrives, consumers
 // wait) and empty[b] (consumers arrive, producer waits).
+#ifndef RL_BLOCKS128
+#define RL_BLOCKS128 4  // resident 128-item tiles per SM the register budget is set for
+#endif
 template <int NT>
-__global__ void __launch_bounds__(NT + kProducerThreads, 512 / NT)
+__global__ void __launch_bounds__(NT + kProducerThreads, NT == 128 ? RL_BLOCKS128 : 2 * RL_BLOCKS128)
     tile_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ double4 smem_raw[];
   constexpr int NALL = NT + kProducerThreads;
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int j = tid; j < 256; j += NALL) s_T1[j] = exp2((double)j * (1.0 / 256.0));
+  for (int j = tid; j < kTabN; j += NALL) s_T1[j] = exp2((double)j * (1.0 / kTabN));
+  if (tid < 2 * kTileBufs)
+    mbar_init((uint32_t)__cvta_generic_to_shared(&s_mbar[tid]), tid < kTileBufs ? kProducerWarps : NT / 32);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   const TileDesc td = P.tiles[blockIdx.x];
   const int ray = td.ray, l0 = td.l0, nlc = td.nlc;
   const unsigned g0 = td.g0, g1 = td.g1;
@@ -998,17 +1069,19 @@ __global__ void __launch_bounds__(NT + kProducerThreads, 512 / NT)
   if (tid >= NT) {
     // ---------------- producer warp ----------------
     __syncthreads();  // (exp tables; keeps the barrier-0 count uniform)
-    producer_loop(P, smem0, bufbytes, nch, nlc, l0, n0, N, nchunks, lane, NALL);
+    producer_loop(P, smem0, bufbytes, nch, nlc, l0, n0, N, nchunks, tid - NT, NALL);
     return;
   }
 
   // ---------------- consumers ----------------
   // my item: g0 + tid; surplus threads shadow the tile's first item and store nothing
   Item it;
+  bool mine;
   {
     const unsigned *off = P.item_off + (size_t)ray * P.nl;
     const unsigned base = off[0];
     unsigned my = g0 + tid;
+    mine = my < g1;
     if (my >= g1) my = g0;
     int a = l0, b = l0 + nlc;
     while (b - a > 1) {
@@ -1028,13 +1101,15 @@ __global__ void __launch_bounds__(NT + kProducerThreads, 512 / NT)
   int r0ok = 0;
   __syncthreads();  // exp tables
   for (int c = 0, b = 0; c < nchunks; c++, b = (b + 1 == kTileBufs) ? 0 : b + 1) {
-    bar_sync(1 + b, NALL);  // full[b]
+    mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar[b]), (uint32_t)((c / kTileBufs) & 1));  // full[b]
     const int c0 = 1 + c * nch;
     integrate_chunk(P, make_buf(b), nlc, min(nch, N - c0), it, l0, r0ok);
-    if (c + kTileBufs < nchunks) bar_arrive(1 + kTileBufs + b, NALL);  // empty[b]
+    __syncwarp();
+    if (lane == 0 && c + kTileBufs < nchunks)
+      mbar_arrive((uint32_t)__cvta_generic_to_shared(&s_mbar[kTileBufs + b]));  // empty[b]
   }
   unsigned long long r = 0, x = 0;
-  if (g0 + tid < g1) {
+  if (mine) {
     const int2 mt = s_meta[tid];
     const int ch = mt.y & 0x3fffffff;
     const size_t row = (size_t)mt.x * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);

@@ -17,6 +17,30 @@ constexpr int kTileIpt = 1;        // ray-channel items per tile_kernel thread
 constexpr int kTileChunk = 31;     // nodes staged per chunk (upper bound: chunk + 1 previous node = one per producer lane)
 constexpr int kSpanThreads = 128;  // span_kernel block = lines per batch upper bound (one mask bit per line)
 
+// exp table of the integrate kernel: 2^(j / kTabN), j = 0..kTabN-1.  16 entries of 8 bytes span the 32
+// shared-memory banks exactly once, so the per-lane lookups never conflict (a 256-entry table cost ~5.6
+// data-pipe wavefronts per lookup on B200; this one costs 2); the polynomial is two or three terms longer.
+#ifndef RL_TAB_BITS
+#define RL_TAB_BITS 4
+#endif
+constexpr int kTabBits = RL_TAB_BITS;
+constexpr int kTabN = 1 << kTabBits;
+#if RL_TAB_BITS == 4
+constexpr double kTabSqrtScale = 4.804489635145799;  // sqrt(kTabN / ln 2)
+constexpr unsigned kHiUmax = 0x40564f52u;             // hi word of sqrt(345 kTabN / ln 2): exp(-345) ~ 1e-150
+constexpr int kDegGauss = 5, kDegTau = 7;             // |r| <= ln2/32: r^6/720 < 1.5e-13, r^8/40320 < 2e-18
+#elif RL_TAB_BITS == 5
+constexpr double kTabSqrtScale = 6.7945744023041525;
+constexpr unsigned kHiUmax = 0x405f8d08u;
+constexpr int kDegGauss = 5, kDegTau = 6;
+#elif RL_TAB_BITS == 8
+constexpr double kTabSqrtScale = 19.217958540583197;
+constexpr unsigned kHiUmax = 0x40764f52u;
+constexpr int kDegGauss = 3, kDegTau = 4;             // |r| <= ln2/512: r^4/24 < 1.5e-13, r^5/120 < 4e-17
+#else
+#error "RL_TAB_BITS must be 4, 5 or 8"
+#endif
+
 // node flags (low 2 bits = tr_icross: 1 = R crossing, 2 = theta crossing, 3 = extra point)
 constexpr uint32_t kFlagIcrMask = 3u;
 constexpr uint32_t kFlagInit = 4u;   // carried profile state is reset before this segment
@@ -82,7 +106,7 @@ struct LineDev {
   // derived constants (host): line.F:2301 aa = k_aa * width ; line.F:4571-4588 j_l = c_src N_up phi,
   // alpha_l = c_alp (N_down B_du - N_up B_ud) phi
   double k_aa, c_src, c_alp, inv_nu0;
-  double kia;  // sqrt(2^18/ln 2) / k_aa: scaled reciprocal Doppler width per unit 1/width (tile_kernel)
+  double kia;  // sqrt(kTabN/ln 2) / k_aa: scaled reciprocal Doppler width per unit 1/width (tile_kernel)
 };
 
 // one tile_kernel block: items [g0, g1) of ray `ray`'s item list, which belong to the nlc lines
