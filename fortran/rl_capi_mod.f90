@@ -89,5 +89,24 @@ module rl_capi_mod
        real(c_double), intent(out) :: tau_center(*), velo(*)
        integer(c_int), intent(out) :: maserflag(*)
      end function
+     ! multi-GPU by camera-ring block (one process per GPU): rings ring_lo..ring_hi, 0 = central beam
+     integer(c_int) function rl_render_rings(ctx, iline0, nl, nfr, vmax_kms, dist_cm, ring_lo, ring_hi, &
+          ringsum, imcir) bind(c, name='rl_render_rings')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: iline0, nl, nfr, ring_lo, ring_hi
+       real(c_double), value :: vmax_kms, dist_cm
+       real(c_double), intent(out) :: ringsum(*)   ! (nfr, 0:nrr, nl)
+       type(c_ptr), value :: imcir                 ! c_null_ptr when the cube is not wanted
+     end function
+     integer(c_int) function rl_flux_from_rings(ctx, nl, nfr, dist_cm, ringsum, flux) &
+          bind(c, name='rl_flux_from_rings')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: nl, nfr
+       real(c_double), value :: dist_cm
+       real(c_double), intent(in) :: ringsum(*)
+       real(c_double), intent(out) :: flux(*)
+     end function
   end interface
 end module rl_capi_mod
