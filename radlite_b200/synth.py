@@ -274,7 +274,8 @@ def config(n: int, *, nr=None, nth=None, nlines=None, nphi=None, nrext=None) -> 
                        vmax_kms=50.0, dv_kms=0.5025, molname="13co", molweight=29.0,
                        abund0=1.0e-4 / 70.0)
     elif n == 4:
-        mol = rovib_molecule(9, 60, band=(4.6, 5.0), nlines=nlines or 500)
+        # "~500 lines": every v<=9, J<=60 fundamental/hot-band line inside 4.6-5.0 um (442 of them)
+        mol = rovib_molecule(9, 60, band=(4.6, 5.0), nlines=nlines)
         m = make_model("cfg4_12CO_nlte_500", nr or 200, nth or 80, mol, tvib_cap=1000.0,
                        freezeout_k=20.0)
     elif n == 5:
