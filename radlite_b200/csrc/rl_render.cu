@@ -766,42 +766,31 @@ constexpr int kMaxTileLines = 64;
 __shared__ LineC s_linec[kMaxTileLines];
 __shared__ NodeRec s_nodes[2][32];
 
-// the global loads one (node, line) pair needs up front: two stencil cells (extra points, crossing
-// type 3, fetch their other two when interpolating)
-struct PairLoads {
-  double4 a, b;
-};
-__device__ __forceinline__ PairLoads pair_issue(const double4 *__restrict__ cellL, size_t nl, const NodeRec *nd) {
-  PairLoads L;
-  const int icr = (int)(((uint32_t)nd->cells.x >> kCellFlagShift) & kFlagIcrMask);
-  L.a = ldg4(cellL + (size_t)(nd->cells.x & kCellMask) * nl);
-  L.b = ldg4(cellL + (size_t)(icr == 2 ? nd->cells.z : nd->cells.y) * nl);
-  return L;
+// (node, line) pair staging.  Nodes on a grid line (crossing types 1 and 2) interpolate between two
+// stencil cells, extra points (type 3) between four (line.F:4054-4197, same expressions as gather_line).
+// The two kinds are staged in separate, compacted passes so that the four-cell arithmetic never runs
+// in a mostly idle warp.
+__device__ __forceinline__ int node_icr(const NodeRec *nd) {
+  return (int)(((uint32_t)nd->cells.x >> kCellFlagShift) & kFlagIcrMask);
 }
-// line.F:4054-4197 (same expressions as gather_line)
-__device__ __forceinline__ double4 pair_interp(const PairLoads &L, const double4 *__restrict__ cellL, size_t nl,
-                                               const NodeRec *nd) {
-  const int icr = (int)(((uint32_t)nd->cells.x >> kCellFlagShift) & kFlagIcrMask);
+__device__ __forceinline__ double4 interp2(const double4 a, const double4 b, double w) {
   double4 o;
-  if (icr != 3) {
-    const double w = (icr == 2) ? nd->wr : nd->wt;
-    o.x = (1.0 - w) * L.a.x + w * L.b.x;
-    o.y = (1.0 - w) * L.a.y + w * L.b.y;
-    o.z = (1.0 - w) * L.a.z + w * L.b.z;
-    o.w = (1.0 - w) * L.a.w + w * L.b.w;
-  } else {
-    const double4 c = ldg4(cellL + (size_t)nd->cells.z * nl), d = ldg4(cellL + (size_t)nd->cells.w * nl);
-    const double dr = nd->wr, dt = nd->wt;
-    o.x = (1.0 - dr) * ((1.0 - dt) * L.a.x + dt * L.b.x) + dr * ((1.0 - dt) * c.x + dt * d.x);
-    o.y = (1.0 - dr) * ((1.0 - dt) * L.a.y + dt * L.b.y) + dr * ((1.0 - dt) * c.y + dt * d.y);
-    o.z = (1.0 - dr) * ((1.0 - dt) * L.a.z + dt * L.b.z) + dr * ((1.0 - dt) * c.z + dt * d.z);
-    o.w = (1.0 - dr) * ((1.0 - dt) * L.a.w + dt * L.b.w) + dr * ((1.0 - dt) * c.w + dt * d.w);
-  }
+  o.x = (1.0 - w) * a.x + w * b.x;
+  o.y = (1.0 - w) * a.y + w * b.y;
+  o.z = (1.0 - w) * a.z + w * b.z;
+  o.w = (1.0 - w) * a.w + w * b.w;
   return o;
 }
-__device__ __forceinline__ void pair_store(const TileBuf &B, int p, int slot, int m, int node,
-                                           const NodeRec *chunk_nodes, const double4 v, int subgrid) {
-  const NodeRec &nd = chunk_nodes[slot];
+__device__ __forceinline__ double4 interp4(const double4 a, const double4 b, const double4 c, const double4 d,
+                                           double dr, double dt) {
+  double4 o;
+  o.x = (1.0 - dr) * ((1.0 - dt) * a.x + dt * b.x) + dr * ((1.0 - dt) * c.x + dt * d.x);
+  o.y = (1.0 - dr) * ((1.0 - dt) * a.y + dt * b.y) + dr * ((1.0 - dt) * c.y + dt * d.y);
+  o.z = (1.0 - dr) * ((1.0 - dt) * a.z + dt * b.z) + dr * ((1.0 - dt) * c.z + dt * d.z);
+  o.w = (1.0 - dr) * ((1.0 - dt) * a.w + dt * b.w) + dr * ((1.0 - dt) * c.w + dt * d.w);
+  return o;
+}
+__device__ __forceinline__ void pair_store(const TileBuf &B, int p, int m, const NodeRec &nd, const double4 v) {
   const LineC lc = s_linec[m];
   ColdLine c;
   c.cN = lc.c_src * v.z;
@@ -816,24 +805,27 @@ __device__ __forceinline__ void pair_store(const TileBuf &B, int p, int slot, in
   h.K1 = c.kk * norm;
   smem_ptr<HotLine>(B.hl)[p] = h;
   smem_ptr<ColdLine>(B.cl)[p] = c;
-  if (m == 0) {
-    HotNode a;
-    a.hds = 0.5 * nd.ds;
-    uint32_t fl = ((uint32_t)nd.cells.x >> kCellFlagShift) & ~kFlagIcrMask;
-    if (!subgrid) fl &= ~kFlagSub;
-    if (node == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
-    a.flags = fl;
-    a.pad = 0;
-    smem_ptr<HotNode>(B.hn)[slot] = a;
-    ColdNode b;
-    // mean width of the segment ending here (slot 0 only serves as a start point: never read)
-    const double lw_prev = (slot > 0) ? chunk_nodes[slot - 1].lw : nd.lw;
-    b.ds = nd.ds;
-    b.dvmu = nd.dvmu;
-    b.lwav = 0.5 * (lw_prev + nd.lw);
-    b.pad = 0.0;
-    smem_ptr<ColdNode>(B.cn)[slot] = b;
-  }
+}
+// per-node part of a staged slot (one lane per slot)
+__device__ __forceinline__ void node_store(const TileBuf &B, int slot, int node, const NodeRec *chunk_nodes,
+                                           int subgrid) {
+  const NodeRec &nd = chunk_nodes[slot];
+  HotNode a;
+  a.hds = 0.5 * nd.ds;
+  uint32_t fl = ((uint32_t)nd.cells.x >> kCellFlagShift) & ~kFlagIcrMask;
+  if (!subgrid) fl &= ~kFlagSub;
+  if (node == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
+  a.flags = fl;
+  a.pad = 0;
+  smem_ptr<HotNode>(B.hn)[slot] = a;
+  ColdNode b;
+  // mean width of the segment ending here (slot 0 only serves as a start point: never read)
+  const double lw_prev = (slot > 0) ? chunk_nodes[slot - 1].lw : nd.lw;
+  b.ds = nd.ds;
+  b.dvmu = nd.dvmu;
+  b.lwav = 0.5 * (lw_prev + nd.lw);
+  b.pad = 0.0;
+  smem_ptr<ColdNode>(B.cn)[slot] = b;
 }
 
 // the producer warp: stages chunk after chunk (nodes c0-1 .. c0+cnt-1 -> slots 0 .. cnt) into the
@@ -886,28 +878,52 @@ __device__ __noinline__ void producer_loop(const RenderParams &P, uint32_t smem0
     B.cl = B.cn + (uint32_t)((nch + 1) * sizeof(ColdNode));
     const NodeRec *cn = s_nodes[c & 1];
     const int npair = (cnt + 1) * nlc;
-    // kPairsInFlight pairs per lane and round, all their gathers in flight together; consecutive
-    // lanes take consecutive lines of one node: with the cell-major layout their records are contiguous
     const size_t nl = (size_t)P.nl;
     const double4 *cell0 = P.cellL + l0;
+    // per-node part, one lane per slot; which slots are extra points (four-cell stencil)
+    const int lane = plane & 31;
+    const bool mine = lane <= cnt;
+    const uint32_t mask3 = __ballot_sync(0xffffffffu, mine && node_icr(cn + lane) == 3);
+    if (plane <= cnt) node_store(B, plane, c0 - 1 + plane, cn, P.subgrid);
+    // pass 1: pairs on grid lines.  kPairsInFlight pairs per lane and round with their gathers in flight
+    // together; consecutive lanes take consecutive lines of one node: with the cell-major layout their
+    // records are contiguous
     for (int p = plane; p < npair; p += kPairsInFlight * NP) {
       int slot[kPairsInFlight], m[kPairsInFlight];
       bool has[kPairsInFlight];
-      PairLoads L[kPairsInFlight];
+      double4 a[kPairsInFlight], b[kPairsInFlight];
 #pragma unroll
       for (int k = 0; k < kPairsInFlight; k++) {
         const int q = p + NP * k;
-        has[k] = q < npair;
-        slot[k] = has[k] ? (int)(((uint32_t)q * Mdiv) >> 20) : 0;
-        m[k] = has[k] ? q - slot[k] * nlc : 0;
-        L[k] = pair_issue(cell0 + m[k], nl, cn + slot[k]);
+        slot[k] = (q < npair) ? (int)(((uint32_t)q * Mdiv) >> 20) : 0;
+        m[k] = q - slot[k] * nlc;
+        has[k] = (q < npair) && !((mask3 >> slot[k]) & 1u);
+        if (has[k]) {
+          const NodeRec *nd = cn + slot[k];
+          const int4 cl = nd->cells;
+          a[k] = ldg4(cell0 + m[k] + (size_t)(cl.x & kCellMask) * nl);
+          b[k] = ldg4(cell0 + m[k] + (size_t)((((uint32_t)cl.x >> kCellFlagShift) & kFlagIcrMask) == 2 ? cl.z : cl.y) * nl);
+        }
       }
 #pragma unroll
       for (int k = 0; k < kPairsInFlight; k++) {
-        if (has[k])
-          pair_store(B, p + NP * k, slot[k], m[k], c0 - 1 + slot[k], cn,
-                     pair_interp(L[k], cell0 + m[k], nl, cn + slot[k]), P.subgrid);
+        if (has[k]) {
+          const NodeRec &nd = cn[slot[k]];
+          pair_store(B, p + NP * k, m[k], nd, interp2(a[k], b[k], node_icr(&nd) == 2 ? nd.wr : nd.wt));
+        }
       }
+    }
+    // pass 2: the extra points of the chunk, compacted
+    const int n3 = __popc(mask3) * nlc;
+    for (int q = plane; q < n3; q += NP) {
+      const int k3 = (int)(((uint32_t)q * Mdiv) >> 20), m3 = q - k3 * nlc;
+      const int slot3 = (int)__fns(mask3, 0, k3 + 1);
+      const NodeRec &nd = cn[slot3];
+      const int4 cl = nd.cells;
+      const double4 *base = cell0 + m3;
+      const double4 a = ldg4(base + (size_t)(cl.x & kCellMask) * nl), b = ldg4(base + (size_t)cl.y * nl);
+      const double4 c4 = ldg4(base + (size_t)cl.z * nl), d = ldg4(base + (size_t)cl.w * nl);
+      pair_store(B, slot3 * nlc + m3, m3, nd, interp4(a, b, c4, d, nd.wr, nd.wt));
     }
     __threadfence_block();
     __syncwarp();
