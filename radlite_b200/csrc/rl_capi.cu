@@ -123,12 +123,14 @@ struct rl_ctx {
   // render buffers
   DevBuf<double4> d_cellL;
   DevBuf<LineDev> d_lines;
-  DevBuf<double> d_line_dnu, d_velo, d_star_line, d_isrf_line;
+  DevBuf<double> d_line_dnu, d_velo, d_velz, d_star_line, d_isrf_line;
   DevBuf<int> d_lev_up, d_lev_down, d_inudust;
   DevBuf<double> d_wgt, d_freq, d_ld_src, d_ld_alp;
   DevBuf<int4> d_rng;
   DevBuf<CellMask> d_masks;
   DevBuf<TileDesc> d_tiles;
+  DevBuf<ZTile> d_ztiles;
+  DevBuf<unsigned short> d_zlines;
   DevBuf<unsigned char> d_dense;
   DevBuf<unsigned int> d_nitems, d_item_off, d_ncta, d_cta_off;
   DevBuf<unsigned char> d_scan_tmp;
@@ -730,6 +732,13 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     CU(c->d_lines.upload(lines, c->st));
     CU(c->d_line_dnu.upload(line_dnu, c->st));
     CU(c->d_velo.upload(velo, c->st));
+    // line.F:462-469 without nu0: dnu_k / nu0 is the same velocity grid for every line
+    std::vector<double> velz(nfr);
+    {
+      const double pv = 3.33567e-6 * vmax_kms, dv = 2.0 * pv / (nfr - 1.0);
+      for (int k = 0; k < nfr; k++) velz[k] = (0.0 - pv) + k * dv;
+    }
+    CU(c->d_velz.upload(velz, c->st));
     CU(c->d_star_line.upload(star, c->st));
     CU(c->d_isrf_line.upload(isrf, c->st));
     CU(c->d_lev_up.upload(lup, c->st));
@@ -826,6 +835,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.lines = c->d_lines.p;
     P.line_dnu = c->d_line_dnu.p;
     P.velo = c->d_velo.p;
+    P.velz = c->d_velz.p;
     P.star_line = c->d_star_line.p;
     P.isrf_line = c->d_isrf_line.p;
     P.rng = c->d_rng.p;
@@ -840,6 +850,19 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.smem_budget = tile_smem_limit(tile_threads);
     P.tile_max_lines = tile_max_lines(tile_threads);
     P.tiles = nullptr;
+    P.use_z = 1;
+    if (const char *e = getenv("RL_KERNEL")) P.use_z = strcmp(e, "tile") != 0;  // tuning experiments
+    P.zlw = 16;
+    if (const char *e = getenv("RL_ZLW")) P.zlw = atoi(e);
+    {
+      int z = 1;
+      while (2 * z <= std::min(32, std::max(1, P.zlw))) z *= 2;
+      P.zlw = z;
+    }
+    P.ztiles = nullptr;
+    P.nztile = 0;
+    CU(c->d_zlines.ensure(ntask));
+    P.zlines = c->d_zlines.p;
     P.img = c->d_img.p;
     P.integ = want_mask ? c->d_integ.p : nullptr;
     P.tau_center = c->d_tau.p;
@@ -872,6 +895,9 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     CU(cudaStreamSynchronize(c->st));
     CU(c->d_tiles.ensure(std::max<size_t>(1, total_ctas)));
     P.tiles = c->d_tiles.p;
+    CU(c->d_ztiles.ensure(std::max<size_t>(1, total_ctas)));
+    P.ztiles = c->d_ztiles.p;
+    P.nztile = total_ctas;
     if (total_ctas) {
       launch_plan(P, true, c->st);
       c->launches++;

@@ -1151,6 +1151,390 @@ __global__ void __launch_bounds__(NT + kProducerThreads, NT == 128 ? RL_BLOCKS12
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// ztile_kernel: the formal solution with the LINES of a batch across the lanes of a warp.
+//
+// The argument of the line profile, (dnu - nu0 Omega.v/c) / (3.33567e-6 nu0 lwav) (line.F:4559-4566,
+// 2301), does not depend on the line: every line of a render shares the velocity grid of the passband
+// (line.F:462-469: dnu_k = nu0 * 3.33567e-6 * v_k) and the local width, so nu0 cancels.  The Gaussian
+// is therefore evaluated once per (ray, node, channel) -- cooperatively by the lanes of the warp, into a
+// small shared-memory table -- and not once per (ray, node, channel, line) as the reference does.
+//
+// One warp = one ray x up to 32 lines (one per lane; with fewer lines per tile the lane pattern repeats
+// and the repeats take different channels) x up to kZCw channels per thread, intensities in registers.
+// Per node every thread gathers and interpolates the cells of ITS line once (coalesced: the lines of a
+// cell are contiguous in cellL; the loads of the next node are in flight while this one is integrated),
+// folds everything that does not depend on the channel into six constants
+//     dtau = D + P e0 + Q e1 ,  theomax = Th + R e0 + S e1       (e0, e1: profile at the two nodes)
+// and then walks its channels, three at a time: independent dependency chains, no per-channel state but
+// the intensity.  The case split of transfer.F:1517,1542 is a warp vote per group of three channels:
+// all lanes thin (dtau <= 1e-9: about 70 % of all steps in disk atmospheres) -> I <- I (1 - dtau) +
+// theomax, else the branch-free full qdr_src_2 step.  Nodes flagged by the geometry (first segment,
+// inner hole / star mixing, 6q > 1 sub-grid candidates) go through zflagged, out of line.
+// There is no block-level synchronisation: the warps of a block are independent tiles.
+// ------------------------------------------------------------------------------------------
+constexpr double kIanScale = kTabSqrtScale / 3.33567e-6;  // scaled reciprocal Doppler width per 1/lwav
+
+struct ZVal {  // channel-independent values of one line at one node
+  double sd, ad;  // dust source / opacity (line.F:4058-4063)
+  double cN, kk;  // c_src N_up ; c_alp (N_down B_du - N_up B_ud)
+};
+struct ZSeg {  // a flagged segment of one line, handed to zflagged through local memory
+  double ds, lwav, dv0, dv1, ian;
+  double nrm0, nrm1;  // profile norm 0.5642/aa of the previous segment (carried state) and of this one
+  ZVal v0, v1;
+};
+
+__device__ __forceinline__ ZVal zvals(const double4 v, double c_src, double cb_du, double cb_ud) {
+  ZVal o;
+  o.sd = v.x;
+  o.ad = v.y;
+  o.cN = c_src * v.z;
+  o.kk = fma(v.w, cb_du, -(v.z * cb_ud));
+  return o;
+}
+
+// flagged segment of one line for the cw channels of a thread (Ic in/out).  ep_a / ec_a: shared-window
+// addresses of the thread's profile values at the two nodes.  Channel of slot c: list position
+// min(jb + c gw, jmax).  Returns the maser bits (telescope.F:4295); xtra += the extra element
+// integrations of sub-gridded segments (real items only).
+__device__ __noinline__ unsigned zflagged(double *Ic, const ZSeg &g, uint32_t fl, int cw, uint32_t ep_a,
+                                          uint32_t ec_a, const LineDev *__restrict__ L,
+                                          const double *__restrict__ dnu_l, const double *__restrict__ star_l,
+                                          const double *__restrict__ velo, int jb, int gw, int jmax, int cmin,
+                                          double starfract, unsigned realbits, unsigned &xtra) {
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
+  const double nu0 = __ldg(&L->nu0), k_aa = __ldg(&L->k_aa), inv_nu0 = __ldg(&L->inv_nu0);
+  const double ds = g.ds;
+  unsigned mb = 0;
+  for (int c = 0; c < cw; c++) {
+    const int j = min(jb + c * gw, jmax);
+    const int ch = j ? cmin + j - 1 : 0;
+    const double dnu = __ldg(dnu_l + ch);
+    const double ep = lds_f64(ep_a + 8u * (uint32_t)c), ec = lds_f64(ec_a + 8u * (uint32_t)c);
+    double inten = Ic[c];
+    int init = 0;
+    if (fl & (kFlagInit | kFlagStar | kFlagZero)) {
+      if (fl & kFlagZero) inten = 0.0;
+      if (fl & kFlagStar) inten = (1.0 - starfract) * inten + starfract * __ldg(star_l + ch);
+      init = 1;
+    }
+    double srcl0 = g.v0.cN * (g.nrm0 * ep), alpl0 = g.v0.kk * (g.nrm0 * ep);  // carried state (line.F:4613-4615)
+    bool done = false, ms = false;
+    if (fl & kFlagSub) {  // line.F:4706-4745
+      const double q = fabs((g.dv1 - g.dv0) / (g.lwav / 2.99792458e5));
+      const double s_c = ds * (dnu * inv_nu0 - g.dv0) / (g.dv1 - g.dv0);
+      const double dls3 = 3.0 * (ds / q);
+      const double sright = s_c + dls3, sleft = s_c - dls3;
+      if (sright > 0.0 && sleft < ds) {
+        const int n = subgrid_tile(nu0, k_aa, dnu, inten, ds, sleft, sright, g.v0.sd, g.v0.ad, g.v0.cN, g.v0.kk,
+                                   g.dv0, g.v1.sd, g.v1.ad, g.v1.cN, g.v1.kk, g.dv1, g.lwav, srcl0, alpl0, init);
+        ms = alpl0 * ds < (double)(-0.01f);
+        if ((realbits >> c) & 1u) xtra += (unsigned)(n - 1);
+        done = true;
+      }
+    }
+    if (!done) {
+      if (init) {  // line.F:4559-4586: the start point with this segment's width
+        const double vel = __ldg(velo + ch);
+        const double e0 = gauss_tab(fma(vel, g.ian, -(g.dv0 * g.ian)), T1, 0);
+        srcl0 = g.v0.cN * (g.nrm1 * e0);
+        alpl0 = g.v0.kk * (g.nrm1 * e0);
+      }
+      const double src0 = g.v0.sd + srcl0, alp0 = g.v0.ad + alpl0;
+      const double r0 = div_fast(src0, alp0);
+      const double alpl1 = g.v1.kk * (g.nrm1 * ec);
+      const double src1 = fma(g.v1.cN, g.nrm1 * ec, g.v1.sd), alp1 = g.v1.ad + alpl1;
+      const double hds = 0.5 * ds;
+      const double dtau = hds * (alp0 + alp1), theomax = hds * (src0 + src1);
+      double r1;
+      full_step(inten, alp0, r0, src1, alp1, r1, dtau, theomax, T1, 0);
+      ms = alpl1 * ds < (double)(-0.01f);
+    }
+    if (ms) mb |= 1u << c;
+    Ic[c] = inten;
+  }
+  return mb;
+}
+
+#ifndef RL_ZMINB
+#define RL_ZMINB 8  // resident blocks per SM the register budget is set for (8: 128 registers)
+#endif
+template <int CW>
+__global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB) ztile_kernel(const __grid_constant__ RenderParams P) {
+  __shared__ double s_et[kZWarps][kZTab];
+  __shared__ NodeRec s_nd[kZWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < kTabN) s_T1[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kTabN));
+  __syncthreads();
+  const unsigned tix = blockIdx.x * kZWarps + warp;
+  if (tix >= P.nztile) return;
+  const ZTile t = P.ztiles[tix];
+  const int ray = t.ray, lws = t.lwshift, gws = 5 - lws, GW = 1 << gws;
+  const int ls = lane & ((1 << lws) - 1), g = lane >> lws;
+  const bool lineok = ls < (int)t.nlt;
+  const int l = (int)P.zlines[t.loff + (lineok ? ls : 0)];
+  const int nchk = t.nchk, j0 = t.j0, cmin = t.cmin;
+  const int cw = (nchk + GW - 1) >> gws;  // channels per thread
+  const int cw3 = 3 * ((cw + 2) / 3);
+  const int jmax = j0 + nchk - 1, jb = j0 + g;
+  // channel of my slot c: position min(jb + c GW, jmax) of the list {0, cmin, cmin + 1, ...}
+  auto chan_of = [&](int c) {
+    const int j = min(jb + c * GW, jmax);
+    return j ? cmin + j - 1 : 0;
+  };
+  const int4 rg = P.rng[(long long)ray * P.nl + l];
+  unsigned realbits = 0;  // slots that are channels the reference integrates for this line
+#pragma unroll
+  for (int c = 0; c < CW; c++) {
+    if (lineok && c * GW + g < nchk) {
+      const int ch = chan_of(c);
+      if (ch == 0 || (ch >= rg.x && ch <= rg.y) || ch == rg.z) realbits |= 1u << c;
+    }
+  }
+  const LineDev *Lp = P.lines + l;
+  const double c_src = __ldg(&Lp->c_src);
+  const double cb_du = __ldg(&Lp->c_alp) * __ldg(&Lp->bdu), cb_ud = __ldg(&Lp->c_alp) * __ldg(&Lp->bud);
+  const double knorm = 0.56419583546 / __ldg(&Lp->k_aa);
+  double I[CW];
+#pragma unroll
+  for (int c = 0; c < CW; c++)
+    I[c] = (P.out_itype == 3) ? __ldg(&P.isrf_line[(size_t)l * P.nfr + chan_of(c)]) : __ldg(&Lp->i_outer);
+
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
+  const uint32_t et0 = (uint32_t)__cvta_generic_to_shared(&s_et[warp][0]);
+  NodeRec *snd = s_nd[warp];
+  const long long n0 = P.node_off[ray];
+  const int N = (int)(P.node_off[ray + 1] - n0);
+  const NodeRec *__restrict__ rec = P.nodes.rec + n0;
+  const double4 *__restrict__ cl = P.cellL + l;
+  const size_t nl = (size_t)P.nl;
+  const int cwS = cw3 | 1;  // table columns per channel group (odd: the groups' reads never conflict)
+  const int NB = min(30, kZTab / (GW * cwS) - 1);  // nodes per batch
+  const uint32_t rowB = (uint32_t)(GW * cwS) * 8u;  // bytes of one node's row of the profile table
+  const uint32_t Mdiv = ((1u << 20) + (uint32_t)cw3 - 1u) / (uint32_t)cw3;
+  unsigned mbits = 0, xtra = 0;
+
+  // the two (four for extra points) stencil cells of a node; the first pair is pulled into L1 one node
+  // ahead (no registers held across the channel loop)
+  auto prefetch = [&](const int4 cells) {
+    const uint32_t icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(cl + (size_t)(cells.x & kCellMask) * nl));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl));
+  };
+  auto gather = [&](const int4 cells, double wr, double wt) {
+    const uint32_t icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
+    const double4 a = ldg4(cl + (size_t)(cells.x & kCellMask) * nl);
+    if (icr == 3) {
+      const double4 b = ldg4(cl + (size_t)cells.y * nl);
+      const double4 c4 = ldg4(cl + (size_t)cells.z * nl), d4 = ldg4(cl + (size_t)cells.w * nl);
+      return interp4(a, b, c4, d4, wr, wt);
+    }
+    const double4 b = ldg4(cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl);
+    return interp2(a, b, icr == 2 ? wr : wt);
+  };
+  ZVal v0;
+  v0.sd = v0.ad = v0.cN = v0.kk = 0.0;
+  double nrm0 = 0.0;  // profile norm of the segment that ended at the previous node
+  if (N > 0) {
+    v0 = zvals(gather(__ldg(&rec[0].cells), __ldg(&rec[0].wr), __ldg(&rec[0].wt)), c_src, cb_du, cb_ud);
+    nrm0 = knorm * __ldg(&rec[0].inv_lwav);
+  }
+  for (int c0 = 1; c0 < N; c0 += NB) {
+    const int cnt = min(NB, N - c0);
+    __syncwarp();  // the previous batch is consumed
+    {  // nodes c0-1 .. c0+cnt (the last one only as look-ahead for the gathers) -> shared memory
+      const int nstage = min(cnt + 2, N - (c0 - 1));
+      if (lane < nstage) {
+        const int4 *src = reinterpret_cast<const int4 *>(rec + (c0 - 1 + lane));
+        int4 *dst = reinterpret_cast<int4 *>(snd + lane);
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k] = __ldg(src + k);
+      }
+    }
+    __syncwarp();
+    prefetch(snd[1].cells);
+    {  // profile table of the batch: rows = nodes c0-1 .. c0+cnt-1, columns = (channel group, slot)
+      const int tot = (cnt + 1) * GW * cw3;
+      for (int idx = lane; idx < tot; idx += 32) {
+        const int tq = (int)(((uint32_t)idx * Mdiv) >> 20);  // idx / cw3 (exact: idx < 2^10)
+        const int c = idx - tq * cw3, gg = tq & (GW - 1), s = tq >> gws;
+        const int j = min(j0 + gg + c * GW, jmax);
+        const double vel = __ldg(P.velz + (j ? cmin + j - 1 : 0));
+        const double ian = snd[s].inv_lwav * kIanScale;
+        const double e = gauss_tab(fma(vel, ian, -(snd[s].dvmu * ian)), T1, 0);
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(et0 + (uint32_t)(((s << gws) + gg) * cwS + c) * 8u), "d"(e)
+                     : "memory");
+      }
+    }
+    __syncwarp();
+    for (int s = 1; s <= cnt; s++) {
+      const NodeRec *nd = snd + s;
+      const int4 cells = nd->cells;
+      uint32_t fl = ((uint32_t)cells.x >> kCellFlagShift) & ~kFlagIcrMask;
+      if (!P.subgrid) fl &= ~kFlagSub;
+      if (c0 - 1 + s == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
+      const ZVal v1 = zvals(gather(cells, nd->wr, nd->wt), c_src, cb_du, cb_ud);
+      if (c0 + s < N) prefetch(snd[s + 1].cells);
+      const double ds = nd->ds;
+      const double nrm1 = knorm * nd->inv_lwav;
+      const uint32_t ep_a = et0 + (uint32_t)(((s - 1) << gws) + g) * (uint32_t)(cwS * 8);
+      const uint32_t ec_a = ep_a + rowB;
+      if (fl == 0) {
+        const double hds = 0.5 * ds;
+        const double hn0 = hds * nrm0, hn1 = hds * nrm1;
+        const double D = hds * (v0.ad + v1.ad), Th = hds * (v0.sd + v1.sd);
+        const double Pq = hn0 * v0.kk, Q = hn1 * v1.kk, R = hn0 * v0.cN, S = hn1 * v1.cN;
+        const bool neg = v1.kk < 0.0;  // inverted populations: full path, which carries the maser test
+#pragma unroll
+        for (int cb = 0; cb < CW; cb += 3) {
+          if (cb < cw) {
+            double ep[3], ec[3], dtau[3], theo[3];
+            bool work = neg;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              ep[k] = lds_f64(ep_a + 8u * (uint32_t)(cb + k));
+              ec[k] = lds_f64(ec_a + 8u * (uint32_t)(cb + k));
+              dtau[k] = fma(Pq, ep[k], fma(Q, ec[k], D));
+              theo[k] = fma(R, ep[k], fma(S, ec[k], Th));
+              // dtau > 1e-9 (REAL literal, transfer.F:1542) as an integer compare of the bit patterns: same
+              // order for positive values, false for negative ones; keeps the FP64 pipe for the arithmetic
+              work = work | (__double_as_longlong(dtau[k]) > __double_as_longlong((double)1e-9f));
+            }
+            if (!__any_sync(0xffffffffu, work)) {
+              // transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau
+#pragma unroll
+              for (int k = 0; k < 3; k++) I[cb + k] = fma(I[cb + k], 1.0 - dtau[k], theo[k]);
+            } else {
+              const double K0 = v0.kk * nrm0, A0 = v0.cN * nrm0, K1 = v1.kk * nrm1, A1 = v1.cN * nrm1;
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                const double alp1 = fma(K1, ec[k], v1.ad), src1 = fma(A1, ec[k], v1.sd);
+                const double alp0 = fma(K0, ep[k], v0.ad), src0 = fma(A0, ep[k], v0.sd);
+                const double r0 = div_fast(src0, alp0);
+                double r1, x, q;
+                step_coeffs(alp0, r0, src1, alp1, r1, dtau[k], theo[k], T1, x, q);
+                I[cb + k] = fma(I[cb + k], x, q);
+                if (neg && (K1 * ec[k]) * ds < (double)(-0.01f)) mbits |= 1u << (cb + k);  // telescope.F:4295
+              }
+            }
+          }
+        }
+      } else {
+        double tmp[CW];
+#pragma unroll
+        for (int c = 0; c < CW; c++) tmp[c] = I[c];
+        ZSeg sg;
+        sg.ds = ds;
+        sg.lwav = 0.5 * (snd[s - 1].lw + nd->lw);
+        sg.dv0 = snd[s - 1].dvmu;
+        sg.dv1 = nd->dvmu;
+        sg.ian = nd->inv_lwav * kIanScale;
+        sg.nrm0 = nrm0;
+        sg.nrm1 = nrm1;
+        sg.v0 = v0;
+        sg.v1 = v1;
+        mbits |= zflagged(tmp, sg, fl, cw, ep_a, ec_a, Lp, P.line_dnu + (size_t)l * P.nfr,
+                          P.star_line + (size_t)l * P.nfr, P.velz, jb, GW, jmax, cmin, P.starfract, realbits, xtra);
+#pragma unroll
+        for (int c = 0; c < CW; c++) I[c] = tmp[c];
+      }
+      v0 = v1;
+      nrm0 = nrm1;
+    }
+  }
+  // results: only the slots that are channels the reference integrates for this line
+  unsigned long long r = 0;
+  const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
+#pragma unroll
+  for (int c = 0; c < CW; c++) {
+    if ((realbits >> c) & 1u) {
+      const int ch = chan_of(c);
+      P.img[row * P.nfr + ch] = I[c];
+      if (P.sparse && I[c] == 0.0) P.dense[(long long)ray * P.nl + l] = 2;  // see fill_sparse_kernel
+      if (P.integ) {
+        const bool masked = P.nonredundant ? (ch != rg.z) : (ch == 0);  // telescope.F:548,575
+        P.integ[row * P.nfr + ch] = masked ? 1 : 2;
+      }
+      r++;
+    }
+  }
+  if (mbits & realbits) atomicOr(&P.maser[l], 1);
+  // work counters: every item walks the ray's N-1 segments; sub-gridding adds extra elements
+  unsigned long long sct = r * (unsigned long long)(N > 0 ? N - 1 : 0), e = sct + xtra;
+  for (int o = 16; o; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    sct += __shfl_xor_sync(0xffffffffu, sct, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  if (lane == 0 && r) {
+    atomicAdd(&P.counters[0], r);
+    atomicAdd(&P.counters[1], e);
+    atomicAdd(&P.counters[2], sct);
+  }
+}
+
+// tiles of ztile_kernel, one thread per ray.  The lines that carry a channel window on this ray (in index
+// order, compacted into zlines) are cut into groups of zlw; the channel list of a group is
+// {0} + [min lo, max hi] over its lines (a superset of every line's own item channels -- the kernel
+// stores only those), cut into chunks when a thread would get more than kZCw channels.  Lines that only
+// need channel 0 (and possibly their first skipped channel) follow, 32 per tile.  FILL = false counts the
+// tiles of every ray, FILL = true (after the scan) writes them.
+template <bool FILL>
+__global__ void zplan_kernel(RenderParams P) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray > P.nray) return;
+  unsigned n = 0;
+  if (ray < P.nray) {
+    const int4 *rg = P.rng + (size_t)ray * P.nl;
+    const unsigned *ni = P.nitems + (size_t)ray * P.nl;
+    unsigned short *zl = P.zlines + (size_t)ray * P.nl;
+    ZTile *out = FILL ? P.ztiles + P.cta_off[ray] : nullptr;
+    auto emit = [&](int start, int cnt, int cmin, int cmax) {
+      if (cmax < cmin) { cmin = 1; cmax = 0; }
+      const int nch = 1 + (cmax - cmin + 1);
+      int lws = 0;
+      while ((1 << lws) < cnt) lws++;
+      const int maxch = (32 >> lws) * kZCw;
+      const int nchunk = (nch + maxch - 1) / maxch, per = (nch + nchunk - 1) / nchunk;
+      for (int j0 = 0; j0 < nch; j0 += per) {
+        if (FILL) {
+          ZTile t;
+          t.ray = ray;
+          t.loff = (unsigned)((size_t)ray * P.nl + start);
+          t.cmin = (unsigned short)cmin;
+          t.j0 = (unsigned short)j0;
+          t.nchk = (unsigned short)min(per, nch - j0);
+          t.nlt = (unsigned char)cnt;
+          t.lwshift = (unsigned char)lws;
+          out[n] = t;
+        }
+        n++;
+      }
+    };
+    int na = 0;
+    for (int pass = 0; pass < 2; pass++) {  // 0: lines with a channel window, 1: the others
+      const int gsz = pass ? 32 : P.zlw;
+      int gstart = na, cmin = 0x7fffffff, cmax = -1;
+      for (int l = 0; l < P.nl; l++) {
+        if (!ni[l]) continue;
+        const int4 r = rg[l];
+        if ((r.y < r.x) != (pass == 1)) continue;
+        if (FILL) zl[na] = (unsigned short)l;
+        if (r.y >= r.x) { cmin = min(cmin, r.x); cmax = max(cmax, r.y); }
+        if (r.z >= 0) { cmin = min(cmin, r.z); cmax = max(cmax, r.z); }
+        na++;
+        if (na - gstart == gsz) {
+          emit(gstart, gsz, cmin, cmax);
+          gstart = na; cmin = 0x7fffffff; cmax = -1;
+        }
+      }
+      if (na > gstart) emit(gstart, na - gstart, cmin, cmax);
+    }
+  }
+  if (!FILL) P.ncta[ray] = n;
+}
+
 // the centre ray (telescope.F:498-527): one thread per (line, channel), reference-ordered scalar
 // path; also yields char_tau_center
 __global__ void __launch_bounds__(128) center_kernel(RenderParams P) {
@@ -1420,6 +1804,11 @@ void launch_span(const RenderParams &P, cudaStream_t st) {
   span_kernel<<<(unsigned)P.nray, kSpanThreads, 0, st>>>(P);
 }
 void launch_plan(const RenderParams &P, bool fill, cudaStream_t st) {
+  if (P.use_z) {
+    if (fill) zplan_kernel<true><<<(P.nray + 1 + 127) / 128, 128, 0, st>>>(P);
+    else zplan_kernel<false><<<(P.nray + 1 + 127) / 128, 128, 0, st>>>(P);
+    return;
+  }
   if (fill) plan_kernel<true><<<(P.nray + 1 + 127) / 128, 128, 0, st>>>(P);
   else plan_kernel<false><<<(P.nray + 1 + 127) / 128, 128, 0, st>>>(P);
 }
@@ -1444,6 +1833,10 @@ int tile_max_lines(int threads) {
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
   if (P.ring_lo <= 0) center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);
   if (!total_ctas) return;
+  if (P.use_z) {
+    ztile_kernel<kZCw><<<(total_ctas + kZWarps - 1) / kZWarps, 32 * kZWarps, 0, st>>>(P);
+    return;
+  }
   if (P.tile_threads == 128) tile_kernel<128><<<total_ctas, 128 + kProducerThreads, P.smem_budget, st>>>(P);
   else tile_kernel<64><<<total_ctas, 64 + kProducerThreads, P.smem_budget, st>>>(P);
 }

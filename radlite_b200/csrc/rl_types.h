@@ -117,6 +117,19 @@ struct __align__(16) TileDesc {
   unsigned short l0, nlc;
 };
 
+// one ztile_kernel warp: ray `ray` x the nlt lines zlines[loff .. loff+nlt) (one line per lane, the lane
+// pattern repeated 32 >> lwshift times) x the channels of list positions j0 .. j0+nchk-1, where the
+// ray's channel list is {0, cmin, cmin+1, ...}
+struct __align__(16) ZTile {
+  int ray;
+  unsigned loff;
+  unsigned short cmin, j0, nchk;
+  unsigned char nlt, lwshift;
+};
+constexpr int kZCw = 9;         // channels per ztile_kernel thread (three groups of three)
+constexpr int kZTab = 1024;     // profile-table entries per warp
+constexpr int kZWarps = 2;      // warps (= tiles) per ztile_kernel block
+
 // per cell, one bit per line of the batch: N_up + N_down surely above / surely below LEVTHRES
 struct __align__(16) CellMask {
   uint4 on, off;
@@ -140,6 +153,7 @@ struct RenderParams {
   const LineDev *lines;      // [nl]
   const double *line_dnu;    // [nl][nfr]
   const double *velo;        // [nl][nfr]
+  const double *velz;        // [nfr] channel velocities / c of the passband, the same for every line (ztile_kernel)
   const double *star_line;   // [nl][nfr]
   const double *isrf_line;   // [nl][nfr]
   // per task (line_local*nray + ray)
@@ -153,6 +167,11 @@ struct RenderParams {
   int tile_threads;          // threads per tile_kernel block (64 or 128) = most items of a tile
   int tile_max_lines;        // most lines a tile may span (shared-memory stage)
   TileDesc *tiles;           // [total tiles] written by plan_kernel<true>
+  int use_z;                 // 1: ztile_kernel (lines across lanes), 0: tile_kernel
+  int zlw;                   // lines per ztile_kernel tile (power of two <= 32)
+  ZTile *ztiles;             // [nztile] written by zplan_kernel<true>
+  unsigned short *zlines;    // [nray][nl] per ray: the lines with a channel window, then the others
+  unsigned nztile;
   CellMask *masks;           // [ncell]
   int sparse;                // 1: skipped channels are not materialised in img (spectrum only)
   unsigned char *dense;      // [ntask] sparse mode: row was completed by fill_kernel
