@@ -1258,10 +1258,10 @@ __device__ __noinline__ unsigned zflagged(double *Ic, const ZSeg &g, uint32_t fl
 }
 
 #ifndef RL_ZMINB
-#define RL_ZMINB 8  // resident blocks per SM the register budget is set for (8: 128 registers)
+#define RL_ZMINB 6  // resident blocks per SM the register budget is set for (6: 168 registers, no hot-loop spills)
 #endif
 template <int CW>
-__global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB) ztile_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_kernel(const __grid_constant__ RenderParams P) {
   __shared__ double s_et[kZWarps][kZTab];
   __shared__ NodeRec s_nd[kZWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

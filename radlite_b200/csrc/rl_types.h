@@ -128,7 +128,10 @@ struct __align__(16) ZTile {
 };
 constexpr int kZCw = 9;         // channels per ztile_kernel thread (three groups of three)
 constexpr int kZTab = 1024;     // profile-table entries per warp
-constexpr int kZWarps = 2;      // warps (= tiles) per ztile_kernel block
+#ifndef RL_ZWARPS
+#define RL_ZWARPS 1
+#endif
+constexpr int kZWarps = RL_ZWARPS;  // warps (= tiles) per ztile_kernel block
 
 // per cell, one bit per line of the batch: N_up + N_down surely above / surely below LEVTHRES
 struct __align__(16) CellMask {
