@@ -1257,11 +1257,31 @@ __device__ __noinline__ unsigned zflagged(double *Ic, const ZSeg &g, uint32_t fl
   return mb;
 }
 
+#ifndef RL_ZPIPE
+#define RL_ZPIPE 1
+#endif
+#ifndef RL_ZPD
+#define RL_ZPD 1  // how many nodes ahead the stencil cells are requested
+#endif
+#if RL_ZPIPE && RL_ZPD != 1
+#error "RL_ZPIPE needs RL_ZPD == 1"
+#endif
+#ifndef RL_ZFAST
+#define RL_ZFAST 1
+#endif
+#ifndef RL_ZSTREAM
+#define RL_ZSTREAM 1
+#endif
 #ifndef RL_ZMINB
 #define RL_ZMINB 6  // resident blocks per SM the register budget is set for (6: 168 registers, no hot-loop spills)
 #endif
 template <int CW>
-__global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_kernel(const __grid_constant__ RenderParams P) {
+#ifdef RL_ZMAXREG
+__global__ void __maxnreg__(RL_ZMAXREG) ztile_kernel
+#else
+__global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_kernel
+#endif
+(const __grid_constant__ RenderParams P) {
   __shared__ double s_et[kZWarps][kZTab];
   __shared__ NodeRec s_nd[kZWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1310,41 +1330,58 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
   const double4 *__restrict__ cl = P.cellL + l;
   const size_t nl = (size_t)P.nl;
   const int cwS = cw3 | 1;  // table columns per channel group (odd: the groups' reads never conflict)
-  const int NB = min(30, kZTab / (GW * cwS) - 1);  // nodes per batch
+  const int NB = min(31 - RL_ZPD, kZTab / (GW * cwS) - 1);  // nodes per batch
   const uint32_t rowB = (uint32_t)(GW * cwS) * 8u;  // bytes of one node's row of the profile table
   const uint32_t Mdiv = ((1u << 20) + (uint32_t)cw3 - 1u) / (uint32_t)cw3;
   unsigned mbits = 0, xtra = 0;
+  constexpr long long kThin = 0x3E112E0BE0000000LL;  // bit pattern of (double)1e-9f (transfer.F:1542, REAL literal)
+  constexpr long long kMid = 0x3EB0C6F7A0B5ED8DLL;   // bit pattern of 1e-6 (transfer.F:1517)
 
   // the two (four for extra points) stencil cells of a node; the first pair is pulled into L1 one node
   // ahead (no registers held across the channel loop)
+  // RL_ZPIPE = 1: the loads of the next node's first cell pair are issued before the channel loop of this
+  // node and consumed after it (eight registers per cell in flight); RL_ZPIPE = 0: they are only pulled
+  // into L1 (RL_ZPD nodes ahead)
+  double4 pa, pb;
   auto prefetch = [&](const int4 cells) {
     const uint32_t icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(cl + (size_t)(cells.x & kCellMask) * nl));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl));
+    const double4 *qa = cl + (size_t)(cells.x & kCellMask) * nl;
+    const double4 *qb = cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl;
+#if RL_ZPIPE
+    pa = ldg4(qa);
+    pb = ldg4(qb);
+#else
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(qa));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(qb));
+#endif
   };
   auto gather = [&](const int4 cells, double wr, double wt) {
     const uint32_t icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
-    const double4 a = ldg4(cl + (size_t)(cells.x & kCellMask) * nl);
+#if !RL_ZPIPE
+    pa = ldg4(cl + (size_t)(cells.x & kCellMask) * nl);
+    pb = ldg4(cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl);
+#endif
     if (icr == 3) {
-      const double4 b = ldg4(cl + (size_t)cells.y * nl);
       const double4 c4 = ldg4(cl + (size_t)cells.z * nl), d4 = ldg4(cl + (size_t)cells.w * nl);
-      return interp4(a, b, c4, d4, wr, wt);
+      return interp4(pa, pb, c4, d4, wr, wt);
     }
-    const double4 b = ldg4(cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl);
-    return interp2(a, b, icr == 2 ? wr : wt);
+    return interp2(pa, pb, icr == 2 ? wr : wt);
   };
   ZVal v0;
   v0.sd = v0.ad = v0.cN = v0.kk = 0.0;
   double nrm0 = 0.0;  // profile norm of the segment that ended at the previous node
   if (N > 0) {
+#if RL_ZPIPE
+    prefetch(__ldg(&rec[0].cells));
+#endif
     v0 = zvals(gather(__ldg(&rec[0].cells), __ldg(&rec[0].wr), __ldg(&rec[0].wt)), c_src, cb_du, cb_ud);
     nrm0 = knorm * __ldg(&rec[0].inv_lwav);
   }
   for (int c0 = 1; c0 < N; c0 += NB) {
     const int cnt = min(NB, N - c0);
     __syncwarp();  // the previous batch is consumed
-    {  // nodes c0-1 .. c0+cnt (the last one only as look-ahead for the gathers) -> shared memory
-      const int nstage = min(cnt + 2, N - (c0 - 1));
+    {  // nodes c0-1 .. c0+cnt-1+RL_ZPD (the last ones only as look-ahead for the gathers) -> shared memory
+      const int nstage = min(cnt + 1 + RL_ZPD, N - (c0 - 1));
       if (lane < nstage) {
         const int4 *src = reinterpret_cast<const int4 *>(rec + (c0 - 1 + lane));
         int4 *dst = reinterpret_cast<int4 *>(snd + lane);
@@ -1353,7 +1390,15 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
       }
     }
     __syncwarp();
-    prefetch(snd[1].cells);
+#if RL_ZPIPE
+    if (c0 == 1) prefetch(snd[1].cells);  // later batches: in flight since the previous batch's last node
+#else
+    if (c0 == 1) {
+#pragma unroll
+      for (int k = 1; k <= RL_ZPD; k++)
+        if (k < N) prefetch(snd[k].cells);
+    }
+#endif
     {  // profile table of the batch: rows = nodes c0-1 .. c0+cnt-1, columns = (channel group, slot)
       const int tot = (cnt + 1) * GW * cw3;
       for (int idx = lane; idx < tot; idx += 32) {
@@ -1375,7 +1420,7 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
       if (!P.subgrid) fl &= ~kFlagSub;
       if (c0 - 1 + s == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
       const ZVal v1 = zvals(gather(cells, nd->wr, nd->wt), c_src, cb_du, cb_ud);
-      if (c0 + s < N) prefetch(snd[s + 1].cells);
+      if (c0 - 1 + s + RL_ZPD < N) prefetch(snd[s + RL_ZPD].cells);
       const double ds = nd->ds;
       const double nrm1 = knorm * nd->inv_lwav;
       const uint32_t ep_a = et0 + (uint32_t)(((s - 1) << gws) + g) * (uint32_t)(cwS * 8);
@@ -1386,36 +1431,75 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
         const double D = hds * (v0.ad + v1.ad), Th = hds * (v0.sd + v1.sd);
         const double Pq = hn0 * v0.kk, Q = hn1 * v1.kk, R = hn0 * v0.cN, S = hn1 * v1.cN;
         const bool neg = v1.kk < 0.0;  // inverted populations: full path, which carries the maser test
+#if RL_ZFAST
+        // the profile is <= 1: if D + |P| + |Q| <= 1e-9 on every lane, every channel of the node takes the
+        // thin branch of transfer.F:1522-1524,1545 (Q = theomax, xp = 1 - dtau): no votes, no branches, all
+        // channels' chains independent
+        const bool maybe = neg | (__double_as_longlong(D + fabs(Pq) + fabs(Q)) > kThin);
+        if (cw3 == CW && !__any_sync(0xffffffffu, maybe)) {
 #pragma unroll
-        for (int cb = 0; cb < CW; cb += 3) {
-          if (cb < cw) {
-            double ep[3], ec[3], dtau[3], theo[3];
-            bool work = neg;
+          for (int c = 0; c < CW; c++) {
+            const double ep = lds_f64(ep_a + 8u * (uint32_t)c), ec = lds_f64(ec_a + 8u * (uint32_t)c);
+            const double dtau = fma(Pq, ep, fma(Q, ec, D)), theo = fma(R, ep, fma(S, ec, Th));
+            I[c] = fma(I[c], 1.0 - dtau, theo);
+          }
+        } else
+#endif
+        {
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-              ep[k] = lds_f64(ep_a + 8u * (uint32_t)(cb + k));
-              ec[k] = lds_f64(ec_a + 8u * (uint32_t)(cb + k));
-              dtau[k] = fma(Pq, ep[k], fma(Q, ec[k], D));
-              theo[k] = fma(R, ep[k], fma(S, ec[k], Th));
-              // dtau > 1e-9 (REAL literal, transfer.F:1542) as an integer compare of the bit patterns: same
-              // order for positive values, false for negative ones; keeps the FP64 pipe for the arithmetic
-              work = work | (__double_as_longlong(dtau[k]) > __double_as_longlong((double)1e-9f));
-            }
-            if (!__any_sync(0xffffffffu, work)) {
-              // transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau
-#pragma unroll
-              for (int k = 0; k < 3; k++) I[cb + k] = fma(I[cb + k], 1.0 - dtau[k], theo[k]);
-            } else {
-              const double K0 = v0.kk * nrm0, A0 = v0.cN * nrm0, K1 = v1.kk * nrm1, A1 = v1.cN * nrm1;
+          for (int cb = 0; cb < CW; cb += 3) {
+            if (cb < cw) {
+              double ep[3], ec[3], dtau[3], theo[3];
+              bool work = neg, thin_some = false;
 #pragma unroll
               for (int k = 0; k < 3; k++) {
-                const double alp1 = fma(K1, ec[k], v1.ad), src1 = fma(A1, ec[k], v1.sd);
-                const double alp0 = fma(K0, ep[k], v0.ad), src0 = fma(A0, ep[k], v0.sd);
-                const double r0 = div_fast(src0, alp0);
-                double r1, x, q;
-                step_coeffs(alp0, r0, src1, alp1, r1, dtau[k], theo[k], T1, x, q);
-                I[cb + k] = fma(I[cb + k], x, q);
-                if (neg && (K1 * ec[k]) * ds < (double)(-0.01f)) mbits |= 1u << (cb + k);  // telescope.F:4295
+                ep[k] = lds_f64(ep_a + 8u * (uint32_t)(cb + k));
+                ec[k] = lds_f64(ec_a + 8u * (uint32_t)(cb + k));
+                dtau[k] = fma(Pq, ep[k], fma(Q, ec[k], D));
+                theo[k] = fma(R, ep[k], fma(S, ec[k], Th));
+                // dtau > 1e-9 (REAL literal, transfer.F:1542) as an integer compare of the bit patterns:
+                // same order for positive values, false for negative ones; keeps the FP64 pipe for the
+                // arithmetic
+                work = work | (__double_as_longlong(dtau[k]) > kThin);
+                thin_some = thin_some | !(__double_as_longlong(dtau[k]) > kMid);
+              }
+              if (!__any_sync(0xffffffffu, work)) {
+                // transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau
+#pragma unroll
+                for (int k = 0; k < 3; k++) I[cb + k] = fma(I[cb + k], 1.0 - dtau[k], theo[k]);
+              } else {
+                const double K0 = v0.kk * nrm0, A0 = v0.cN * nrm0, K1 = v1.kk * nrm1, A1 = v1.cN * nrm1;
+#if RL_ZSTREAM
+                // lanes whose dust opacity alone is positive never see alpha <= 0 unless the line inverts
+                const bool odd = neg | thin_some | !(v0.ad > kAlpTiny) | !(v1.ad > kAlpTiny) | (v0.kk < 0.0);
+                if (!__any_sync(0xffffffffu, odd)) {
+                  // every lane: dtau > 1e-6 and both opacities positive -- qdr_src_2 without its case
+                  // selections (the operations of step_coeffs on this branch, bit for bit)
+#pragma unroll
+                  for (int k = 0; k < 3; k++) {
+                    const double alp1 = fma(K1, ec[k], v1.ad), src1 = fma(A1, ec[k], v1.sd);
+                    const double alp0 = fma(K0, ep[k], v0.ad), src0 = fma(A0, ep[k], v0.sd);
+                    const double r0 = div_fast(src0, alp0), r1 = div_fast(src1, alp1);
+                    const double xpe = expneg_tab(dtau[k], T1, 0);
+                    const double e0 = 1.0 - xpe;
+                    const double bt = div_fast(dtau[k] - e0, dtau[k]);
+                    const double qv = fmin(fma(e0 - bt, r0, bt * r1), theo[k]);
+                    I[cb + k] = fma(I[cb + k], xpe, qv);
+                  }
+                } else
+#endif
+                {
+#pragma unroll
+                  for (int k = 0; k < 3; k++) {
+                    const double alp1 = fma(K1, ec[k], v1.ad), src1 = fma(A1, ec[k], v1.sd);
+                    const double alp0 = fma(K0, ep[k], v0.ad), src0 = fma(A0, ep[k], v0.sd);
+                    const double r0 = div_fast(src0, alp0);
+                    double r1, x, q;
+                    step_coeffs(alp0, r0, src1, alp1, r1, dtau[k], theo[k], T1, x, q);
+                    I[cb + k] = fma(I[cb + k], x, q);
+                    if (neg && (K1 * ec[k]) * ds < (double)(-0.01f)) mbits |= 1u << (cb + k);  // telescope.F:4295
+                  }
+                }
               }
             }
           }
