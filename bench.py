@@ -290,7 +290,7 @@ def run_gpu(args):
         except (OSError, KeyError, ValueError):
             pass
         value = R_tot / dev_s_max
-        # dominant kernel: tile_kernel, one launch per step (100 lines fit one batch)
+        # dominant kernel: ztile_kernel, one launch per step (100 lines fit one batch)
         n_launch = args.steps * max(1, -(-nl // max(1, nl)))
         E_rank = cnt["E"]
         achieved_tf = E_rank * FLOP_PER_ELEMENT / (ms[2] * 1e-3) / 1e12
@@ -328,9 +328,9 @@ def run_gpu(args):
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
                          "traffic_source": traffic_src,
-                         "kernel": "tile_kernel<128> (ray x (line, channel) tile formal solution)",
+                         "kernel": "ztile_kernel<9> (formal solution: one warp = one ray x 16 lines across the lanes x 18 channels)",
                          "how": "E element integrations x 64 FP64 flop (SURVEY.md 8d, exp excluded) / CUDA-event "
-                                "time of the integrate phase (tile_kernel + centre ray) on the library's stream; "
+                                "time of the integrate phase (ztile_kernel + centre ray) on the library's stream; "
                                 "peak = DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no "
                                 "FP64 entry); the path is FP64 arithmetic on L2-resident data, so the hbm "
                                 "figure below is reported for completeness only",

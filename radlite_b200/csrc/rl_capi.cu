@@ -850,8 +850,15 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.smem_budget = tile_smem_limit(tile_threads);
     P.tile_max_lines = tile_max_lines(tile_threads);
     P.tiles = nullptr;
-    P.use_z = 1;
-    if (const char *e = getenv("RL_KERNEL")) P.use_z = strcmp(e, "tile") != 0;  // tuning experiments
+    // integrate kernel by regime: with several lines per batch the lanes of a warp take lines and share
+    // the line-independent profile (ztile_kernel); single-line renders (BASELINE configs 1, 3) spread
+    // (line, channel) items over the threads of a block fed by a staging warp (tile_kernel).
+    // RL_KERNEL=z|tile forces one of them (parity tests run both on every model).
+    P.use_z = nb >= 8 ? 1 : 0;
+    if (const char *e = getenv("RL_KERNEL")) {
+      if (!strcmp(e, "tile")) P.use_z = 0;
+      else if (!strcmp(e, "z")) P.use_z = 1;
+    }
     P.zlw = 16;
     if (const char *e = getenv("RL_ZLW")) P.zlw = atoi(e);
     {
