@@ -83,6 +83,9 @@ def cpu_sample(ncores, ring_stride, nlines=100):
     return sum(r[0] for r in res), sum(r[1] for r in res), tmax, wall
 
 
+_OUT = sys.stdout
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -117,7 +120,7 @@ def run_reference(args):
                          "element_integrations_per_s": Es / ts},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -341,7 +344,7 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -357,6 +360,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE line, the JSON result: anything libraries print there (NCCL's version
+    # banner, for one) is routed to stderr
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

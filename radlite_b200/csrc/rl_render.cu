@@ -1179,6 +1179,12 @@ struct ZVal {  // channel-independent values of one line at one node
   double sd, ad;  // dust source / opacity (line.F:4058-4063)
   double cN, kk;  // c_src N_up ; c_alp (N_down B_du - N_up B_ud)
 };
+struct __align__(16) ZNx {  // per staged node, derived once by the staging lane
+  uint32_t offA, offB;  // element offsets (cell * nl) of the first stencil pair in cellL
+  uint32_t fl, icr;     // segment flags (sub-grid switch and first-segment flag applied) ; crossing type
+  double w, hds;        // interpolation weight of the pair ; ds / 2
+  double ian, dvi;      // scaled reciprocal Doppler width of the segment ending here ; Omega.v/c times it
+};
 struct ZSeg {  // a flagged segment of one line, handed to zflagged through local memory
   double ds, lwav, dv0, dv1, ian;
   double nrm0, nrm1;  // profile norm 0.5642/aa of the previous segment (carried state) and of this one
@@ -1284,6 +1290,7 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
 (const __grid_constant__ RenderParams P) {
   __shared__ double s_et[kZWarps][kZTab];
   __shared__ NodeRec s_nd[kZWarps][32];
+  __shared__ ZNx s_nx[kZWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < kTabN) s_T1[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kTabN));
   __syncthreads();
@@ -1324,6 +1331,7 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
   const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
   const uint32_t et0 = (uint32_t)__cvta_generic_to_shared(&s_et[warp][0]);
   NodeRec *snd = s_nd[warp];
+  ZNx *snx = s_nx[warp];
   const long long n0 = P.node_off[ray];
   const int N = (int)(P.node_off[ray + 1] - n0);
   const NodeRec *__restrict__ rec = P.nodes.rec + n0;
@@ -1343,38 +1351,53 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
   // node and consumed after it (eight registers per cell in flight); RL_ZPIPE = 0: they are only pulled
   // into L1 (RL_ZPD nodes ahead)
   double4 pa, pb;
-  auto prefetch = [&](const int4 cells) {
-    const uint32_t icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
-    const double4 *qa = cl + (size_t)(cells.x & kCellMask) * nl;
-    const double4 *qb = cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl;
+  auto derive = [&](const int4 cells, double ds, double wr, double wt, double inv_lwav, double dvmu, int node) {
+    ZNx x;
+    x.icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
+    x.offA = (uint32_t)(cells.x & kCellMask) * (uint32_t)nl;
+    x.offB = (uint32_t)(x.icr == 2 ? cells.z : cells.y) * (uint32_t)nl;
+    uint32_t fl = ((uint32_t)cells.x >> kCellFlagShift) & ~kFlagIcrMask;
+    if (!P.subgrid) fl &= ~kFlagSub;
+    if (node == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
+    x.fl = fl;
+    x.w = x.icr == 2 ? wr : wt;
+    x.hds = 0.5 * ds;
+    x.ian = inv_lwav * kIanScale;
+    x.dvi = dvmu * x.ian;
+    return x;
+  };
+  auto prefetch = [&](uint32_t offA, uint32_t offB) {
 #if RL_ZPIPE
-    pa = ldg4(qa);
-    pb = ldg4(qb);
+    pa = ldg4(cl + offA);
+    pb = ldg4(cl + offB);
 #else
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(qa));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(qb));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(cl + offA));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(cl + offB));
 #endif
   };
-  auto gather = [&](const int4 cells, double wr, double wt) {
-    const uint32_t icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
+  // interpolated cell values at a node (x: its derived record, raw: its node record, read only for the
+  // four-cell extra points)
+  auto gather = [&](const ZNx x, const NodeRec *raw) {
 #if !RL_ZPIPE
-    pa = ldg4(cl + (size_t)(cells.x & kCellMask) * nl);
-    pb = ldg4(cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl);
+    pa = ldg4(cl + x.offA);
+    pb = ldg4(cl + x.offB);
 #endif
-    if (icr == 3) {
+    if (x.icr == 3) {
+      const int4 cells = raw->cells;
       const double4 c4 = ldg4(cl + (size_t)cells.z * nl), d4 = ldg4(cl + (size_t)cells.w * nl);
-      return interp4(pa, pb, c4, d4, wr, wt);
+      return interp4(pa, pb, c4, d4, raw->wr, raw->wt);
     }
-    return interp2(pa, pb, icr == 2 ? wr : wt);
+    return interp2(pa, pb, x.w);
   };
   ZVal v0;
   v0.sd = v0.ad = v0.cN = v0.kk = 0.0;
   double nrm0 = 0.0;  // profile norm of the segment that ended at the previous node
   if (N > 0) {
+    const ZNx x0 = derive(__ldg(&rec[0].cells), 0.0, __ldg(&rec[0].wr), __ldg(&rec[0].wt), 1.0, 0.0, 0);
 #if RL_ZPIPE
-    prefetch(__ldg(&rec[0].cells));
+    prefetch(x0.offA, x0.offB);
 #endif
-    v0 = zvals(gather(__ldg(&rec[0].cells), __ldg(&rec[0].wr), __ldg(&rec[0].wt)), c_src, cb_du, cb_ud);
+    v0 = zvals(gather(x0, rec), c_src, cb_du, cb_ud);
     nrm0 = knorm * __ldg(&rec[0].inv_lwav);
   }
   for (int c0 = 1; c0 < N; c0 += NB) {
@@ -1387,16 +1410,18 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
         int4 *dst = reinterpret_cast<int4 *>(snd + lane);
 #pragma unroll
         for (int k = 0; k < 4; k++) dst[k] = __ldg(src + k);
+        const NodeRec *mine = snd + lane;  // (own writes: visible to this lane)
+        snx[lane] = derive(mine->cells, mine->ds, mine->wr, mine->wt, mine->inv_lwav, mine->dvmu, c0 - 1 + lane);
       }
     }
     __syncwarp();
 #if RL_ZPIPE
-    if (c0 == 1) prefetch(snd[1].cells);  // later batches: in flight since the previous batch's last node
+    if (c0 == 1) prefetch(snx[1].offA, snx[1].offB);  // later batches: in flight since the previous batch's last node
 #else
     if (c0 == 1) {
 #pragma unroll
       for (int k = 1; k <= RL_ZPD; k++)
-        if (k < N) prefetch(snd[k].cells);
+        if (k < N) prefetch(snx[k].offA, snx[k].offB);
     }
 #endif
     {  // profile table of the batch: rows = nodes c0-1 .. c0+cnt-1, columns = (channel group, slot)
@@ -1406,8 +1431,7 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
         const int c = idx - tq * cw3, gg = tq & (GW - 1), s = tq >> gws;
         const int j = min(j0 + gg + c * GW, jmax);
         const double vel = __ldg(P.velz + (j ? cmin + j - 1 : 0));
-        const double ian = snd[s].inv_lwav * kIanScale;
-        const double e = gauss_tab(fma(vel, ian, -(snd[s].dvmu * ian)), T1, 0);
+        const double e = gauss_tab(fma(vel, snx[s].ian, -snx[s].dvi), T1, 0);
         asm volatile("st.shared.f64 [%0], %1;" ::"r"(et0 + (uint32_t)(((s << gws) + gg) * cwS + c) * 8u), "d"(e)
                      : "memory");
       }
@@ -1415,18 +1439,15 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
     __syncwarp();
     for (int s = 1; s <= cnt; s++) {
       const NodeRec *nd = snd + s;
-      const int4 cells = nd->cells;
-      uint32_t fl = ((uint32_t)cells.x >> kCellFlagShift) & ~kFlagIcrMask;
-      if (!P.subgrid) fl &= ~kFlagSub;
-      if (c0 - 1 + s == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
-      const ZVal v1 = zvals(gather(cells, nd->wr, nd->wt), c_src, cb_du, cb_ud);
-      if (c0 - 1 + s + RL_ZPD < N) prefetch(snd[s + RL_ZPD].cells);
-      const double ds = nd->ds;
+      const ZNx nx = snx[s];
+      const uint32_t fl = nx.fl;
+      const ZVal v1 = zvals(gather(nx, nd), c_src, cb_du, cb_ud);
+      if (c0 - 1 + s + RL_ZPD < N) prefetch(snx[s + RL_ZPD].offA, snx[s + RL_ZPD].offB);
       const double nrm1 = knorm * nd->inv_lwav;
       const uint32_t ep_a = et0 + (uint32_t)(((s - 1) << gws) + g) * (uint32_t)(cwS * 8);
       const uint32_t ec_a = ep_a + rowB;
       if (fl == 0) {
-        const double hds = 0.5 * ds;
+        const double hds = nx.hds;
         const double hn0 = hds * nrm0, hn1 = hds * nrm1;
         const double D = hds * (v0.ad + v1.ad), Th = hds * (v0.sd + v1.sd);
         const double Pq = hn0 * v0.kk, Q = hn1 * v1.kk, R = hn0 * v0.cN, S = hn1 * v1.cN;
@@ -1497,7 +1518,7 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
                     double r1, x, q;
                     step_coeffs(alp0, r0, src1, alp1, r1, dtau[k], theo[k], T1, x, q);
                     I[cb + k] = fma(I[cb + k], x, q);
-                    if (neg && (K1 * ec[k]) * ds < (double)(-0.01f)) mbits |= 1u << (cb + k);  // telescope.F:4295
+                    if (neg && (K1 * ec[k]) * nd->ds < (double)(-0.01f)) mbits |= 1u << (cb + k);  // telescope.F:4295
                   }
                 }
               }
@@ -1509,11 +1530,11 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
 #pragma unroll
         for (int c = 0; c < CW; c++) tmp[c] = I[c];
         ZSeg sg;
-        sg.ds = ds;
+        sg.ds = nd->ds;
         sg.lwav = 0.5 * (snd[s - 1].lw + nd->lw);
         sg.dv0 = snd[s - 1].dvmu;
         sg.dv1 = nd->dvmu;
-        sg.ian = nd->inv_lwav * kIanScale;
+        sg.ian = nx.ian;
         sg.nrm0 = nrm0;
         sg.nrm1 = nrm1;
         sg.v0 = v0;
