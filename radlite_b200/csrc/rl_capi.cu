@@ -854,10 +854,10 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     // the line-independent profile (ztile_kernel); single-line renders (BASELINE configs 1, 3) spread
     // (line, channel) items over the threads of a block fed by a staging warp (tile_kernel).
     // RL_KERNEL=z|tile forces one of them (parity tests run both on every model).
-    P.use_z = nb >= 8 ? 1 : 0;
+    P.use_z = (nb >= 8 && nfr <= 65535) ? 1 : 0;  // (ZTile carries channel numbers as 16-bit fields)
     if (const char *e = getenv("RL_KERNEL")) {
       if (!strcmp(e, "tile")) P.use_z = 0;
-      else if (!strcmp(e, "z")) P.use_z = 1;
+      else if (!strcmp(e, "z") && nfr <= 65535) P.use_z = 1;
     }
     P.zlw = 16;
     if (const char *e = getenv("RL_ZLW")) P.zlw = atoi(e);
