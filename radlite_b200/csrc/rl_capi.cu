@@ -119,6 +119,7 @@ struct rl_ctx {
   DevBuf<long long> d_node_off;
   std::vector<long long> h_node_off;
   DevBuf<NodeRec> d_nrec;
+  DevBuf<double4> d_light;  // 32-byte per-node scratch of the geometry fill pass
   DevBuf<int> d_status;
   // render buffers
   DevBuf<double4> d_cellL;
@@ -570,6 +571,8 @@ static int ensure_geometry(rl_ctx *c) {
   P.node_cnt = c->d_node_cnt.p;
   P.node_off = nullptr;
   P.nodes = NodesDev{};
+  P.light = nullptr;
+  P.ntot = 0;
   launch_geom(P, true, c->st);
   c->launches++;
   CU(cudaGetLastError());
@@ -587,11 +590,15 @@ static int ensure_geometry(rl_ctx *c) {
   CU(c->d_node_off.upload(c->h_node_off, c->st));
   const size_t n = (size_t)c->total_nodes;
   if ((size_t)c->nr * c->nth > (size_t)kCellMask) return fail(c, 13, "grid has too many cells for the node record");
+  if (c->nr >= 32768 || c->nt >= 32768) return fail(c, 13, "grid has too many points per axis for the node scratch");
   CU(c->d_nrec.ensure(n));
+  CU(c->d_light.ensure(std::max<size_t>(1, n)));
   P.node_off = c->d_node_off.p;
   P.nodes = nodes_dev(c);
+  P.light = c->d_light.p;
+  P.ntot = c->total_nodes;
   launch_geom(P, false, c->st);
-  c->launches++;
+  c->launches += 2;
   CU(cudaGetLastError());
   rcode = check_status(c, "ray geometry, fill pass");
   if (rcode) return rcode;

@@ -126,6 +126,12 @@ __device__ double radius_of_s(const Ray &R, double s) {
   return sqrt(R.x0 * R.x0 + R.z0 * R.z0 + s * s + 2.0 * R.z0 * R.costh0 * s);
 }
 
+__device__ int ir_of_radius(const GridDev &g, double rad) {  // telescope.F:3204-3214
+  if (rad < RCf(g, 1)) return 0;
+  if (rad > RCf(g, g.nr)) return g.nr;
+  return hunt_bisect(g.rc + 2, g.nr, rad);
+}
+
 struct Extra {
   double s, radius, theta;
   int ir, it;
@@ -139,24 +145,33 @@ struct Emit {
   int star_done;
 };
 
-template <bool COUNT>
-__device__ void emit_node(const GeomParams &P, const Ray &R, Emit &E, long long base, int iray,
-                          int icr, double radius, double theta, int ir, int it, double s,
-                          double znew, double bnew) {
-  if (COUNT) {
-    E.n++;
-    return;
-  }
+// A node as the per-ray merge sees it (32 bytes): everything emit needs besides the ray's own constants.
+// The merge (serial along a ray, one thread per ray) only writes these; the trigonometry, the stencil, the
+// velocity projection and the segment bookkeeping of every node are done by node_kernel, one thread per
+// node.  pk = icr | ir << 2 | it << 17.
+struct __align__(16) LightNode {
+  double s, radius, theta;
+  uint32_t pk;
+  int iray;
+};
+
+// the part of a node that does not depend on its neighbours
+struct NodePoint {
+  double dr, dt, lw, dvmu;
+  int4 cells;
+};
+__device__ NodePoint node_point(const GeomParams &P, double x0, double z0, double costh0, double znew, double bnew,
+                                int icr, double radius, double theta, int ir, int it, double s) {
   const GridDev &g = P.g;
-  const long long idx = base + E.n;
+  NodePoint o;
   // local direction (telescope.F:3692-3718)
-  double snew = s + R.z0 * R.costh0;
+  double snew = s + z0 * costh0;
   double mu = snew / sqrt(bnew * bnew + snew * snew);
-  double dummy = bnew * sqrt(bnew * bnew + snew * snew - (znew + snew * R.costh0) * (znew + snew * R.costh0));
+  double dummy = bnew * sqrt(bnew * bnew + snew * snew - (znew + snew * costh0) * (znew + snew * costh0));
   double sinphi;
-  if (dummy > 0.0) sinphi = (bnew * bnew * R.costh0 - znew * snew) / dummy;
+  if (dummy > 0.0) sinphi = (bnew * bnew * costh0 - znew * snew) / dummy;
   else sinphi = 1.e1 * kTelescEps;
-  double phi = (R.x0 < 0.0) ? asin(sinphi) : (kPi - asin(sinphi));
+  double phi = (x0 < 0.0) ? asin(sinphi) : (kPi - asin(sinphi));
   while (phi < 0.0) phi = phi + 2.0 * kPi;
   while (phi >= 2.0 * kPi) phi = phi - 2.0 * kPi;
   // position inside the cell (telescope.F:3955-3958, 4088-4091)
@@ -202,52 +217,141 @@ __device__ void emit_node(const GeomParams &P, const Ray &R, Emit &E, long long 
     }
   }
   if (mu > 1.0) atomicCAS(P.status, 0, 393);  // line.F:2656
-  double dvmu = 3.335668e-11 * (mu * v1 + sqrt(1.0 - mu * mu) * (v2 * sin(phi) + v3 * cos(phi)));
-  // segment bookkeeping (telescope.F:4050-4104, 4129-4193)
+  o.dvmu = 3.335668e-11 * (mu * v1 + sqrt(1.0 - mu * mu) * (v2 * sin(phi) + v3 * cos(phi)));
+  o.dr = dr;
+  o.dt = dt;
+  o.lw = lw;
+  o.cells = cells;
+  return o;
+}
+
+// the record of a node from its own point values and the previous node of the ray (have_prev = false:
+// first node); segment bookkeeping of telescope.F:4050-4104, 4129-4193, sub-grid trigger of line.F:4706-4709
+__device__ NodeRec node_record(const GeomParams &P, int iray, const NodePoint &pt, int icr, int ir, double s,
+                               bool have_prev, double s_prev, int ir_old, int icr_old, double dvmu_prev,
+                               double lw_prev, int &star_done) {
   uint32_t flag = (uint32_t)icr;
   double ds = 0.0;
-  if (E.n > 0) {
-    ds = s - E.s_prev;
+  if (have_prev) {
+    ds = s - s_prev;
     if (ds < 0.0) atomicCAS(P.status, 0, 749);
-    if (ir == 1 && E.ir_old == 1 && icr == 1 && E.icr_old == 1) { ds = 0.0; flag |= kFlagInit; }
+    if (ir == 1 && ir_old == 1 && icr == 1 && icr_old == 1) { ds = 0.0; flag |= kFlagInit; }
     if (!(ir > 1)) {
       if (P.in_itype == 1) {
-        if (E.ir_old == 1 && E.icr_old == 1) flag |= kFlagZero | kFlagInit;
+        if (ir_old == 1 && icr_old == 1) flag |= kFlagZero | kFlagInit;
       } else if (P.in_itype == 2) {
-        if (ir == 1 && !E.star_done && iray == 0 && P.rbeam0_center > 0.0) {
+        if (ir == 1 && !star_done && iray == 0 && P.rbeam0_center > 0.0) {
           if (P.rbeam0_center < P.rstar) atomicCAS(P.status, 0, 124);
           flag |= kFlagStar | kFlagInit;
-          E.star_done = 1;
+          star_done = 1;
         }
       } else {
         atomicCAS(P.status, 0, 13);  // inner BC 0 disabled / unknown (telescope.F:4129-4134, 4210)
       }
     }
   }
-  // sub-grid trigger of the segment ending here (line.F:4706-4709)
-  double inv_lwav = 1.0 / lw;
-  if (E.n > 0) {
-    const double lwseg = 0.5 * (E.lw_prev + lw);
-    const double q = fabs((dvmu - E.dvmu_prev) / (lwseg / 2.99792458e5));
+  double inv_lwav = 1.0 / pt.lw;
+  if (have_prev) {
+    const double lwseg = 0.5 * (lw_prev + pt.lw);
+    const double q = fabs((pt.dvmu - dvmu_prev) / (lwseg / 2.99792458e5));
     if (2.0 * 3.0 * q > 1.0) flag |= kFlagSub;
     inv_lwav = 1.0 / lwseg;
   }
   NodeRec rec;
   rec.ds = ds;
-  rec.dvmu = dvmu;
-  rec.lw = lw;
+  rec.dvmu = pt.dvmu;
+  rec.lw = pt.lw;
   rec.inv_lwav = inv_lwav;
-  rec.wr = dr;
-  rec.wt = dt;
+  rec.wr = pt.dr;
+  rec.wt = pt.dt;
+  int4 cells = pt.cells;
   cells.x |= (int)(flag << kCellFlagShift);
   rec.cells = cells;
-  P.nodes.rec[idx] = rec;
-  E.dvmu_prev = dvmu;
-  E.lw_prev = lw;
+  return rec;
+}
+
+// COUNT: count only.  Otherwise the centre ray (the only one with state that runs along the ray: the
+// star is mixed in once) is finished here, every other ray only leaves its LightNode list.
+template <bool COUNT>
+__device__ void emit_node(const GeomParams &P, const Ray &R, Emit &E, long long base, int iray,
+                          int icr, double radius, double theta, int ir, int it, double s,
+                          double znew, double bnew) {
+  if (COUNT) {
+    E.n++;
+    return;
+  }
+  const long long idx = base + E.n;
+  if (iray != 0) {
+    LightNode ln;
+    ln.s = s;
+    ln.radius = radius;
+    ln.theta = theta;
+    ln.pk = (uint32_t)icr | ((uint32_t)ir << 2) | ((uint32_t)it << 17);
+    ln.iray = iray;
+    static_cast<LightNode *>(P.light)[idx] = ln;
+    E.n++;
+    return;
+  }
+  const NodePoint pt = node_point(P, R.x0, R.z0, R.costh0, znew, bnew, icr, radius, theta, ir, it, s);
+  P.nodes.rec[idx] = node_record(P, iray, pt, icr, ir, s, E.n > 0, E.s_prev, E.ir_old, E.icr_old, E.dvmu_prev,
+                                 E.lw_prev, E.star_done);
+  E.dvmu_prev = pt.dvmu;
+  E.lw_prev = pt.lw;
   E.ir_old = ir;
   E.icr_old = icr;
   E.s_prev = s;
   E.n++;
+}
+
+// one thread per node: the record of node i from its LightNode and the one before it on the same ray
+// (whose point values are simply evaluated again: cheaper than a second pass over the records)
+__global__ void __launch_bounds__(256) node_kernel(GeomParams P, long long ntot) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot) return;
+  if (i < P.node_off[1]) return;  // the centre ray was finished by geom_kernel (its slots hold no LightNode)
+  const LightNode *light = static_cast<const LightNode *>(P.light);
+  const LightNode me = light[i];
+  const int iray = me.iray;
+  const double x0 = P.x0[iray], z0 = P.z0[iray];
+  const double costh0 = cos(P.theta0), sinth0 = sin(P.theta0);
+  const double sinth02 = sinth0 * sinth0;
+  const double znew = z0 * sinth02;
+  const double bnew = sqrt(x0 * x0 + z0 * z0 * sinth02);
+  // theta cell of an R crossing (telescope.F:3331-3344) / radial cell of a theta crossing (:3204-3214)
+  auto complete = [&](const LightNode &n, int &icr, int &ir, int &it, double &theta) {
+    icr = (int)(n.pk & 3u);
+    ir = (int)((n.pk >> 2) & 0x7fffu);
+    it = (int)(n.pk >> 17);
+    theta = n.theta;
+    if (icr == 1) {
+      theta = atan(sqrt(x0 * x0 + sinth02 * n.s * n.s) / (z0 + costh0 * n.s));
+      if (theta < 0.0) theta = theta + kPi;
+      it = hunt_bisect(P.g.tc + 2, P.g.nt, theta);
+    } else if (icr == 2) {
+      ir = ir_of_radius(P.g, n.radius);
+    }
+  };
+  int icr, ir, it;
+  double theta;
+  complete(me, icr, ir, it, theta);
+  const NodePoint pt = node_point(P, x0, z0, costh0, znew, bnew, icr, me.radius, theta, ir, it, me.s);
+  const bool have_prev = i != P.node_off[iray];
+  double s_prev = 0.0, dvmu_prev = 0.0, lw_prev = 0.0;
+  int ir_old = -99, icr_old = -99;
+  if (have_prev) {
+    const LightNode pv = light[i - 1];
+    int it_old;
+    double theta_old;
+    complete(pv, icr_old, ir_old, it_old, theta_old);
+    const NodePoint pp = node_point(P, x0, z0, costh0, znew, bnew, icr_old, pv.radius, theta_old, ir_old, it_old,
+                                    pv.s);
+    s_prev = pv.s;
+    dvmu_prev = pp.dvmu;
+    lw_prev = pp.lw;
+  }
+  int star_done = 1;  // (the star is only ever mixed into the centre ray)
+  P.nodes.rec[i] = node_record(P, iray, pt, icr, ir, me.s, have_prev, s_prev, ir_old, icr_old, dvmu_prev, lw_prev,
+                               star_done);
 }
 
 template <bool COUNT>
@@ -418,6 +522,9 @@ __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
   const double znew = z0 * R.sinth02;
   const double bnew = sqrt(x0 * x0 + z0 * z0 * R.sinth02);
   const long long base = COUNT ? 0 : P.node_off[iray];
+  // rays finished by node_kernel: the bracketing searches of a node (theta cell of an R crossing, radial
+  // cell of a theta crossing) are left to it as well -- they are the expensive serial part of the merge
+  const bool lazy = !COUNT && iray != 0;
   Emit E;
   E.n = 0;
   E.ir_old = -99;
@@ -449,10 +556,8 @@ __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
       double th_rad = radius_of_s(R, th_s);
       if (th_rad <= rmaxt && th_rad >= rmint && (th_s - sprev) > eps * th_rad && th_s >= sbeg &&
           th_s <= send) {
-        int th_ir;
-        if (th_rad < RCf(g, 1)) th_ir = 0;
-        else if (th_rad > RCf(g, nr)) th_ir = nr;
-        else th_ir = hunt_bisect(g.rc + 2, nr, th_rad);
+        int th_ir = 0;
+        if (!lazy) th_ir = ir_of_radius(g, th_rad);
         emit_node<COUNT>(P, R, E, base, iray, 2, th_rad, TCf(g, th_it), th_ir, th_it, th_s, znew, bnew);
         sprev = th_s;
       }
@@ -461,8 +566,12 @@ __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
       else th_s = 1.e30;
     } else {
       if (r_rad <= rmaxr && r_rad >= rminr && (r_s - sprev) > eps * r_rad && r_s >= sbeg && r_s <= send) {
-        double th = theta_of_s(R, r_s);
-        int it = hunt_bisect(g.tc + 2, nt, th);
+        double th = 0.0;
+        int it = 0;
+        if (!lazy) {
+          th = theta_of_s(R, r_s);
+          it = hunt_bisect(g.tc + 2, nt, th);
+        }
         emit_node<COUNT>(P, R, E, base, iray, 1, r_rad, th, r_ix, it, r_s, znew, bnew);
         sprev = r_s;
       }
@@ -479,8 +588,12 @@ __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
 void launch_geom(const GeomParams &P, bool count, cudaStream_t st) {
   const int threads = 128;
   const int blocks = (P.nray + threads - 1) / threads;
-  if (count) geom_kernel<true><<<blocks, threads, 0, st>>>(P);
-  else geom_kernel<false><<<blocks, threads, 0, st>>>(P);
+  if (count) {
+    geom_kernel<true><<<blocks, threads, 0, st>>>(P);
+  } else {
+    geom_kernel<false><<<blocks, threads, 0, st>>>(P);
+    if (P.ntot > 0) node_kernel<<<(unsigned)((P.ntot + 255) / 256), 256, 0, st>>>(P, P.ntot);
+  }
 }
 
 }  // namespace rl

@@ -92,6 +92,8 @@ struct GeomParams {
   const long long *node_off;  // [nray+1] (fill pass)
   int *node_cnt;              // [nray]   (count pass)
   NodesDev nodes;
+  void *light;      // [total nodes] 32-byte LightNode scratch of the fill pass (rl_geom.cu)
+  long long ntot;   // total nodes (fill pass)
   int *status;  // first error code (reference stop code), 0 = ok
 };
 
