@@ -129,6 +129,14 @@ int rl_flux_from_rings(rl_ctx *ctx, int nl, int nfr, double dist_cm, const doubl
  * sub-grid steps), S = ray segments visited. */
 void rl_get_counters(const rl_ctx *ctx, double *R, double *E, double *S);
 void rl_reset_counters(rl_ctx *ctx);
+/* Opaque-wall start (no counterpart in the reference, which integrates every segment of a ray,
+ * telescope.F:4079-4300): segments that lie behind more than `tau` of dust optical depth -- for every
+ * line of the batch, counted from the observer's end of the ray -- are not integrated; what they would
+ * contribute is attenuated by exp(-tau).  Default 150 (a relative 1e-65: far below the rounding of the
+ * result); 0 integrates every segment.  R, E, S above keep counting the reference's work;
+ * rl_get_executed returns the element integrations this library actually performed. */
+int rl_set_wall_tau(rl_ctx *ctx, double tau);
+double rl_get_executed(const rl_ctx *ctx);
 
 /* ---- device-resident variant used by bench.py's kernel-only timing ----------------------
  * Same work as rl_render but inputs stay resident and nothing is copied back: the result stays

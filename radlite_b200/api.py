@@ -90,6 +90,18 @@ class Renderer(Binding):
         self._check(self.lib.rl_flux_from_rings(self.ctx, nl, nfr, float(dist_cm), _d(ringsum), _d(flux)))
         return flux
 
+    def set_wall_tau(self, tau: float):
+        """Opaque-wall start (include/radlite_b200.h): 0 integrates every segment like the reference."""
+        self.lib.rl_set_wall_tau.argtypes = [C.c_void_p, C.c_double]
+        self.lib.rl_set_wall_tau.restype = C.c_int
+        self._check(self.lib.rl_set_wall_tau(self.ctx, float(tau)))
+
+    def executed_elements(self) -> float:
+        """Element integrations actually performed since the last reset_counters()."""
+        self.lib.rl_get_executed.argtypes = [C.c_void_p]
+        self.lib.rl_get_executed.restype = C.c_double
+        return float(self.lib.rl_get_executed(self.ctx))
+
     def invalidate_geometry(self):
         self.lib.rl_invalidate_geometry.argtypes = [C.c_void_p]
         self.lib.rl_invalidate_geometry.restype = None

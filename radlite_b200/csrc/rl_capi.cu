@@ -23,6 +23,7 @@ void launch_prep(const PrepParams &P, cudaStream_t st);
 void launch_span(const RenderParams &P, cudaStream_t st);
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st);
 void launch_plan(const RenderParams &P, bool fill, cudaStream_t st);
+void launch_wall(const RenderParams &P, double *admin, int *inverted, int *nstart, cudaStream_t st);
 int tile_smem_limit(int threads);
 int tile_max_lines(int threads);
 void launch_fill(const RenderParams &P, cudaStream_t st);
@@ -131,6 +132,9 @@ struct rl_ctx {
   DevBuf<CellMask> d_masks;
   DevBuf<TileDesc> d_tiles;
   DevBuf<ZTile> d_ztiles;
+  DevBuf<double> d_admin;   // [ncell] smallest dust opacity of the batch's lines (opaque-wall start)
+  DevBuf<int> d_inverted, d_nstart;
+  double wall_tau = 150.0;  // 0: integrate every segment like the reference does
   DevBuf<unsigned short> d_zlines;
   DevBuf<unsigned char> d_dense;
   DevBuf<unsigned int> d_nitems, d_item_off, d_ncta, d_cta_off;
@@ -197,8 +201,8 @@ int rl_create(rl_ctx **out, int device) {
   }
   for (auto &e : c->ev) cudaEventCreate(&e);
   c->d_status.ensure(1);
-  c->d_counters.ensure(3);
-  cudaMemsetAsync(c->d_counters.p, 0, 3 * sizeof(unsigned long long), c->st);
+  c->d_counters.ensure(4);
+  cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->st);
   cudaStreamSynchronize(c->st);
   *out = c;
   return 0;
@@ -875,6 +879,9 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     }
     P.ztiles = nullptr;
     P.nztile = 0;
+    P.nstart = nullptr;
+    P.wall_tau = c->wall_tau;
+    if (const char *e = getenv("RL_WALL_TAU")) P.wall_tau = atof(e);
     CU(c->d_zlines.ensure(ntask));
     P.zlines = c->d_zlines.p;
     P.img = c->d_img.p;
@@ -885,6 +892,15 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.status = c->d_status.p;
     launch_span(P, c->st);
     c->launches += P.nonredundant ? 2 : 1;
+    if (P.use_z && P.wall_tau > 0.0) {
+      CU(c->d_admin.ensure(ncell));
+      CU(c->d_inverted.ensure(1));
+      CU(c->d_nstart.ensure(c->nray));
+      CU(cudaMemsetAsync(c->d_inverted.p, 0, sizeof(int), c->st));
+      launch_wall(P, c->d_admin.p, c->d_inverted.p, c->d_nstart.p, c->st);
+      c->launches += 2;
+      P.nstart = c->d_nstart.p;
+    }
     {
       size_t tmp_bytes = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_nitems.p, c->d_item_off.p, (int)(ntask + 1), c->st);
@@ -1042,9 +1058,22 @@ void rl_get_counters(const rl_ctx *cc, double *R, double *E, double *S) {
   if (S) *S = (double)h[2];
 }
 
+double rl_get_executed(const rl_ctx *cc) {
+  rl_ctx *c = const_cast<rl_ctx *>(cc);
+  unsigned long long h = 0;
+  cudaSetDevice(c->device);
+  cudaMemcpyAsync(&h, c->d_counters.p + 3, sizeof h, cudaMemcpyDeviceToHost, c->st);
+  cudaStreamSynchronize(c->st);
+  return (double)h;
+}
+int rl_set_wall_tau(rl_ctx *c, double tau) {
+  if (!c) return 13;
+  c->wall_tau = tau > 0.0 ? tau : 0.0;
+  return 0;
+}
 void rl_reset_counters(rl_ctx *c) {
   cudaSetDevice(c->device);
-  cudaMemsetAsync(c->d_counters.p, 0, 3 * sizeof(unsigned long long), c->st);
+  cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->st);
   cudaStreamSynchronize(c->st);
 }
 

@@ -773,21 +773,29 @@ __shared__ NodeRec s_nodes[2][32];
 __device__ __forceinline__ int node_icr(const NodeRec *nd) {
   return (int)(((uint32_t)nd->cells.x >> kCellFlagShift) & kFlagIcrMask);
 }
+// (explicitly rounded products + one fma per component: the same bits at every call site, whatever the
+// compiler's contraction choices -- the opaque-wall start evaluates a node in the prologue of ztile_kernel
+// that the full walk evaluates in its loop body)
+__device__ __forceinline__ double lerp_rn(double a, double b, double w, double w1) {
+  return fma(w, b, __dmul_rn(w1, a));
+}
 __device__ __forceinline__ double4 interp2(const double4 a, const double4 b, double w) {
+  const double w1 = 1.0 - w;
   double4 o;
-  o.x = (1.0 - w) * a.x + w * b.x;
-  o.y = (1.0 - w) * a.y + w * b.y;
-  o.z = (1.0 - w) * a.z + w * b.z;
-  o.w = (1.0 - w) * a.w + w * b.w;
+  o.x = lerp_rn(a.x, b.x, w, w1);
+  o.y = lerp_rn(a.y, b.y, w, w1);
+  o.z = lerp_rn(a.z, b.z, w, w1);
+  o.w = lerp_rn(a.w, b.w, w, w1);
   return o;
 }
 __device__ __forceinline__ double4 interp4(const double4 a, const double4 b, const double4 c, const double4 d,
                                            double dr, double dt) {
+  const double r1 = 1.0 - dr, t1 = 1.0 - dt;
   double4 o;
-  o.x = (1.0 - dr) * ((1.0 - dt) * a.x + dt * b.x) + dr * ((1.0 - dt) * c.x + dt * d.x);
-  o.y = (1.0 - dr) * ((1.0 - dt) * a.y + dt * b.y) + dr * ((1.0 - dt) * c.y + dt * d.y);
-  o.z = (1.0 - dr) * ((1.0 - dt) * a.z + dt * b.z) + dr * ((1.0 - dt) * c.z + dt * d.z);
-  o.w = (1.0 - dr) * ((1.0 - dt) * a.w + dt * b.w) + dr * ((1.0 - dt) * c.w + dt * d.w);
+  o.x = lerp_rn(lerp_rn(a.x, b.x, dt, t1), lerp_rn(c.x, d.x, dt, t1), dr, r1);
+  o.y = lerp_rn(lerp_rn(a.y, b.y, dt, t1), lerp_rn(c.y, d.y, dt, t1), dr, r1);
+  o.z = lerp_rn(lerp_rn(a.z, b.z, dt, t1), lerp_rn(c.z, d.z, dt, t1), dr, r1);
+  o.w = lerp_rn(lerp_rn(a.w, b.w, dt, t1), lerp_rn(c.w, d.w, dt, t1), dr, r1);
   return o;
 }
 __device__ __forceinline__ void pair_store(const TileBuf &B, int p, int m, const NodeRec &nd, const double4 v) {
@@ -1148,6 +1156,7 @@ __global__ void __launch_bounds__(NT + kProducerThreads, NT == 128 ? RL_BLOCKS12
     atomicAdd(&P.counters[0], r);
     atomicAdd(&P.counters[1], e);
     atomicAdd(&P.counters[2], s);
+    atomicAdd(&P.counters[3], e);
   }
 }
 
@@ -1195,8 +1204,8 @@ __device__ __forceinline__ ZVal zvals(const double4 v, double c_src, double cb_d
   ZVal o;
   o.sd = v.x;
   o.ad = v.y;
-  o.cN = c_src * v.z;
-  o.kk = fma(v.w, cb_du, -(v.z * cb_ud));
+  o.cN = __dmul_rn(c_src, v.z);
+  o.kk = fma(v.w, cb_du, -__dmul_rn(v.z, cb_ud));
   return o;
 }
 
@@ -1337,6 +1346,12 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
   const NodeRec *__restrict__ rec = P.nodes.rec + n0;
   const double4 *__restrict__ cl = P.cellL + l;
   const size_t nl = (size_t)P.nl;
+  // first segment to integrate: everything before it lies behind an opaque dust wall (wall_kernel)
+  const int ns = P.nstart ? max(1, min(__ldg(&P.nstart[ray]), N - 1)) : 1;
+  if (ns > 1) {
+#pragma unroll
+    for (int c = 0; c < CW; c++) I[c] = 0.0;
+  }
   const int cwS = cw3 | 1;  // table columns per channel group (odd: the groups' reads never conflict)
   const int NB = min(31 - RL_ZPD, kZTab / (GW * cwS) - 1);  // nodes per batch
   const uint32_t rowB = (uint32_t)(GW * cwS) * 8u;  // bytes of one node's row of the profile table
@@ -1392,15 +1407,16 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
   ZVal v0;
   v0.sd = v0.ad = v0.cN = v0.kk = 0.0;
   double nrm0 = 0.0;  // profile norm of the segment that ended at the previous node
-  if (N > 0) {
-    const ZNx x0 = derive(__ldg(&rec[0].cells), 0.0, __ldg(&rec[0].wr), __ldg(&rec[0].wt), 1.0, 0.0, 0);
+  if (N > 0) {  // values at the node the first integrated segment starts from
+    const NodeRec *r0 = rec + (ns - 1);
+    const ZNx x0 = derive(__ldg(&r0->cells), 0.0, __ldg(&r0->wr), __ldg(&r0->wt), 1.0, 0.0, 0);
 #if RL_ZPIPE
     prefetch(x0.offA, x0.offB);
 #endif
-    v0 = zvals(gather(x0, rec), c_src, cb_du, cb_ud);
-    nrm0 = knorm * __ldg(&rec[0].inv_lwav);
+    v0 = zvals(gather(x0, r0), c_src, cb_du, cb_ud);
+    nrm0 = knorm * __ldg(&r0->inv_lwav);
   }
-  for (int c0 = 1; c0 < N; c0 += NB) {
+  for (int c0 = ns; c0 < N; c0 += NB) {
     const int cnt = min(NB, N - c0);
     __syncwarp();  // the previous batch is consumed
     {  // nodes c0-1 .. c0+cnt-1+RL_ZPD (the last ones only as look-ahead for the gathers) -> shared memory
@@ -1416,12 +1432,12 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
     }
     __syncwarp();
 #if RL_ZPIPE
-    if (c0 == 1) prefetch(snx[1].offA, snx[1].offB);  // later batches: in flight since the previous batch's last node
+    if (c0 == ns) prefetch(snx[1].offA, snx[1].offB);  // later batches: in flight since the previous batch's last node
 #else
-    if (c0 == 1) {
+    if (c0 == ns) {
 #pragma unroll
       for (int k = 1; k <= RL_ZPD; k++)
-        if (k < N) prefetch(snx[k].offA, snx[k].offB);
+        if (c0 - 1 + k < N) prefetch(snx[k].offA, snx[k].offB);
     }
 #endif
     {  // profile table of the batch: rows = nodes c0-1 .. c0+cnt-1, columns = (channel group, slot)
@@ -1565,17 +1581,21 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
     }
   }
   if (mbits & realbits) atomicOr(&P.maser[l], 1);
-  // work counters: every item walks the ray's N-1 segments; sub-gridding adds extra elements
+  // work counters: every item walks the ray's N-1 segments (the reference's count, whether or not an opaque
+  // wall shortened the walk here); sub-gridding adds extra elements; executed = what this kernel integrated
   unsigned long long sct = r * (unsigned long long)(N > 0 ? N - 1 : 0), e = sct + xtra;
+  unsigned long long ex = r * (unsigned long long)(N > ns ? N - ns : 0) + xtra;
   for (int o = 16; o; o >>= 1) {
     e += __shfl_xor_sync(0xffffffffu, e, o);
     sct += __shfl_xor_sync(0xffffffffu, sct, o);
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
     r += __shfl_xor_sync(0xffffffffu, r, o);
   }
   if (lane == 0 && r) {
     atomicAdd(&P.counters[0], r);
     atomicAdd(&P.counters[1], e);
     atomicAdd(&P.counters[2], sct);
+    atomicAdd(&P.counters[3], ex);
   }
 }
 
@@ -1640,6 +1660,63 @@ __global__ void zplan_kernel(RenderParams P) {
   if (!FILL) P.ncta[ray] = n;
 }
 
+// ------------------------------------------------------------------------------------------
+// Opaque-wall start.  Whatever a ray has accumulated before it enters an optically thick dust layer is
+// multiplied by exp(-tau) on the way out: with tau > wall_tau = 150 that is a relative contribution below
+// 1e-65, forty-nine orders of magnitude below the rounding of the result, so the segments in front of
+// the wall (seen from the far end of the ray) need not be integrated.  The bound is line independent and
+// conservative: admin[cell] = the smallest dust opacity any line of the batch has in the cell, interpolated
+// with the node's own weights (all in [0, 1]: a lower bound of every line's interpolated opacity), summed
+// from the observer's end of the ray; line opacity only adds to it (batches with an inverted level pair
+// anywhere are not shortened at all).  The reference integrates those segments (telescope.F:4079-4300 has
+// no such cut); its work counters R, S are reported unchanged, the executed element integrations separately.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wallprep_kernel(RenderParams P, double *admin, int *inverted) {
+  const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= P.ncell) return;
+  double mn = 1.0e300;
+  bool inv = false;
+  for (int l = 0; l < P.nl; l++) {
+    const double4 v = ldg4(P.cellL + (size_t)cell * P.nl + l);
+    mn = fmin(mn, v.y);
+    inv = inv || (v.w * __ldg(&P.lines[l].bdu) - v.z * __ldg(&P.lines[l].bud) < 0.0) || !(v.y >= 0.0);
+  }
+  admin[cell] = mn;
+  if (inv) atomicOr(inverted, 1);
+}
+
+__global__ void __launch_bounds__(128) wall_kernel(RenderParams P, const double *__restrict__ admin,
+                                                   const int *__restrict__ inverted, int *nstart) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= P.nray) return;
+  int ns = 1;
+  const long long n0 = P.node_off[ray];
+  const int N = (int)(P.node_off[ray + 1] - n0);
+  if (ray > 0 && N > 2 && P.wall_tau > 0.0 && !__ldg(inverted)) {
+    const NodeRec *rec = P.nodes.rec + n0;
+    auto amin_at = [&](int n) {
+      const Node nd = load_node(P.nodes.rec, n0 + n);
+      const int icr = nd.flags & kFlagIcrMask;
+      const double a = __ldg(&admin[nd.cells.x]);
+      if (icr == 1) return (1.0 - nd.wt) * a + nd.wt * __ldg(&admin[nd.cells.y]);
+      if (icr == 2) return (1.0 - nd.wr) * a + nd.wr * __ldg(&admin[nd.cells.z]);
+      return (1.0 - nd.wr) * ((1.0 - nd.wt) * a + nd.wt * __ldg(&admin[nd.cells.y])) +
+             nd.wr * ((1.0 - nd.wt) * __ldg(&admin[nd.cells.z]) + nd.wt * __ldg(&admin[nd.cells.w]));
+    };
+    double cum = 0.0, a1 = amin_at(N - 1);
+    for (int n = N - 1; n >= 2; n--) {  // segment n joins nodes n-1 and n
+      const double a0 = amin_at(n - 1);
+      cum += 0.5 * __ldg(&rec[n].ds) * (a0 + a1);
+      if (cum > P.wall_tau) {
+        ns = n;
+        break;
+      }
+      a1 = a0;
+    }
+  }
+  nstart[ray] = ns;
+}
+
 // the centre ray (telescope.F:498-527): one thread per (line, channel), reference-ordered scalar
 // path; also yields char_tau_center
 __global__ void __launch_bounds__(128) center_kernel(RenderParams P) {
@@ -1671,6 +1748,7 @@ __global__ void __launch_bounds__(128) center_kernel(RenderParams P) {
     atomicAdd(&P.counters[0], r);
     atomicAdd(&P.counters[1], e);
     atomicAdd(&P.counters[2], s);
+    atomicAdd(&P.counters[3], e);
   }
 }
 
@@ -1754,6 +1832,7 @@ __device__ __noinline__ void fill_zero_continuum(const RenderParams &P, long lon
     atomicAdd(&P.counters[0], r);
     atomicAdd(&P.counters[1], e);
     atomicAdd(&P.counters[2], s);
+    atomicAdd(&P.counters[3], e);
   }
 }
 
@@ -1907,6 +1986,10 @@ void launch_prep(const PrepParams &P, cudaStream_t st) {
 void launch_span(const RenderParams &P, cudaStream_t st) {
   if (P.nonredundant) mask_kernel<<<(unsigned)((P.ncell * 4 + 255) / 256), 256, 0, st>>>(P);
   span_kernel<<<(unsigned)P.nray, kSpanThreads, 0, st>>>(P);
+}
+void launch_wall(const RenderParams &P, double *admin, int *inverted, int *nstart, cudaStream_t st) {
+  wallprep_kernel<<<(unsigned)((P.ncell + 255) / 256), 256, 0, st>>>(P, admin, inverted);
+  wall_kernel<<<(P.nray + 127) / 128, 128, 0, st>>>(P, admin, inverted, nstart);
 }
 void launch_plan(const RenderParams &P, bool fill, cudaStream_t st) {
   if (P.use_z) {

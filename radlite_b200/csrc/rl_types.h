@@ -184,7 +184,11 @@ struct RenderParams {
   unsigned char *integ;      // [nl][nrow][nfr] 1 = channel was integrated with cmask=1
   double *tau_center;        // [nl]
   int *maser;                // [nl]
-  unsigned long long *counters;  // {R, E, S}
+  unsigned long long *counters;  // {R, E, S, executed element integrations}
+  // opaque-wall start (ztile_kernel): nstart[ray] = first segment that is integrated; the segments before it
+  // lie behind more than wall_tau of dust optical depth for every line of the batch
+  const int *nstart;         // [nray] or null
+  double wall_tau;
   int *status;
 };
 
