@@ -892,7 +892,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.status = c->d_status.p;
     launch_span(P, c->st);
     c->launches += P.nonredundant ? 2 : 1;
-    if (P.use_z && P.wall_tau > 0.0) {
+    if (P.wall_tau > 0.0) {
       CU(c->d_admin.ensure(ncell));
       CU(c->d_inverted.ensure(1));
       CU(c->d_nstart.ensure(c->nray));

@@ -1071,8 +1071,13 @@ __global__ void __launch_bounds__(NT + kProducerThreads, NT == 128 ? RL_BLOCKS12
   const TileDesc td = P.tiles[blockIdx.x];
   const int ray = td.ray, l0 = td.l0, nlc = td.nlc;
   const unsigned g0 = td.g0, g1 = td.g1;
-  const long long n0 = P.node_off[ray];
-  const int N = (int)(P.node_off[ray + 1] - n0);
+  // opaque-wall start (wall_kernel): the walk begins one segment BEFORE the first segment that matters;
+  // that segment, the "first segment of the ray" here, sets up the carried profile state at its end node
+  // exactly (line.F:4613-4615), and whatever it contributes itself lies behind the whole wall
+  const int Nfull = (int)(P.node_off[ray + 1] - P.node_off[ray]);
+  const int shift = P.nstart ? max(0, min(__ldg(&P.nstart[ray]), Nfull - 1) - 2) : 0;
+  const long long n0 = P.node_off[ray] + shift;
+  const int N = Nfull - shift;
   // shared-memory carve-up: kTileBufs buffers of nch+1 slots (+1 phantom slot of hn and hl, see
   // integrate_chunk)
   const int slot_bytes = nlc * kPairBytes + kSlotBytes, ph_bytes = nlc * (int)sizeof(HotLine) + (int)sizeof(HotNode);
@@ -1146,17 +1151,20 @@ __global__ void __launch_bounds__(NT + kProducerThreads, NT == 128 ? RL_BLOCKS12
     x = f >> 8;
   }
   // work counters: every item walks the ray's N-1 segments; sub-gridding adds extra elements
-  unsigned long long s = r * (unsigned long long)(N > 0 ? N - 1 : 0), e = s + x;
+  // (the reference's counts, whether or not an opaque wall shortened the walk; ex = executed elements)
+  unsigned long long s = r * (unsigned long long)(Nfull > 0 ? Nfull - 1 : 0), e = s + x;
+  unsigned long long ex = r * (unsigned long long)(N > 0 ? N - 1 : 0) + x;
   for (int o = 16; o; o >>= 1) {
     e += __shfl_xor_sync(0xffffffffu, e, o);
     s += __shfl_xor_sync(0xffffffffu, s, o);
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
     r += __shfl_xor_sync(0xffffffffu, r, o);
   }
   if (lane == 0 && r) {
     atomicAdd(&P.counters[0], r);
     atomicAdd(&P.counters[1], e);
     atomicAdd(&P.counters[2], s);
-    atomicAdd(&P.counters[3], e);
+    atomicAdd(&P.counters[3], ex);
   }
 }
 

@@ -286,12 +286,8 @@ def test_opaque_wall_start_is_exact(renderer_cls, oracle_cls, integrate_kernel):
     assert np.array_equal(on["image"], off["image"])
     assert c_on["R"] == c_off["R"] and c_on["S"] == c_off["S"] and c_on["E"] <= c_off["E"]
     assert ex_off == c_off["E"]
-    if integrate_kernel == "tile":
-        assert ex_on == ex_off  # tile_kernel walks every segment
-    else:
-        assert ex_on < 0.9 * ex_off, (ex_on, ex_off)  # this disk's midplane is opaque at 4.7 um
+    assert ex_on < 0.9 * ex_off, (ex_on, ex_off)  # this disk's midplane is opaque at 4.7 um
     g.set_wall_tau(1.0)  # an absurdly thin "wall": now the image must change (the cut really is applied)
     thin = g.render(1, 8, m.nfr, m.passband, synth.PARSEC, want_image=True)
-    if integrate_kernel != "tile":
-        assert not np.array_equal(thin["image"], off["image"])
-        assert rel_err(thin["flux"], off["flux"]).max() < 1.0
+    assert not np.array_equal(thin["image"], off["image"])
+    assert rel_err(thin["flux"], off["flux"]).max() < 1.0
