@@ -68,6 +68,16 @@ module rl_capi_mod
        integer(c_int), value :: subgrid, nonredundant
        real(c_double), value :: levthres, aksmax
      end function
+     ! opaque-wall start (include/radlite_b200.h): 0 integrates every segment like the reference; default 150
+     integer(c_int) function rl_set_wall_tau(ctx, tau) bind(c, name='rl_set_wall_tau')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: ctx
+       real(c_double), value :: tau
+     end function
+     real(c_double) function rl_get_executed(ctx) bind(c, name='rl_get_executed')
+       import :: c_ptr, c_double
+       type(c_ptr), value :: ctx
+     end function
      integer(c_int) function rl_get_camera_dims(ctx, nrr, nphi, nray) bind(c, name='rl_get_camera_dims')
        import :: c_ptr, c_int
        type(c_ptr), value :: ctx
