@@ -1,3 +1,4 @@
+"""Opaque-wall start on/off on a small disk: executed-element fraction and bitwise image comparison (GPU)."""
 import sys; sys.path.insert(0,'/root/repo')
 import numpy as np
 from radlite_b200 import synth
