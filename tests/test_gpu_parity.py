@@ -248,6 +248,14 @@ def test_cfg2_full_size_properties(renderer_cls, oracle_cls):
     # flux scales as 1/d^2 exactly (telescope.F:1433)
     out2 = g.render(1, 8, m.nfr, m.passband, 2.0 * synth.PARSEC)
     assert np.array_equal(out2["flux"] * 4.0, f)
+    # opaque-wall start: integrating every segment gives the same spectra, bit for bit
+    g.reset_counters()
+    g.render(1, 8, m.nfr, m.passband, synth.PARSEC)
+    frac_on = g.executed_elements() / g.counters()["E"]
+    g.set_wall_tau(0.0)
+    assert np.array_equal(g.render(1, 8, m.nfr, m.passband, synth.PARSEC)["flux"], f)
+    g.set_wall_tau(150.0)
+    assert 0.3 < frac_on < 0.9, frac_on  # about 40 % of this disk's element integrations lie behind walls
     # rendering lines one by one gives bit-identical spectra (lines are independent)
     one = g.render(5, 1, m.nfr, m.passband, synth.PARSEC)
     assert same_bits(one["flux"][0], f[4])
