@@ -1183,12 +1183,16 @@ __global__ void __launch_bounds__(NT + kProducerThreads, NT == 128 ? RL_BLOCKS12
 // cell are contiguous in cellL; the loads of the next node are in flight while this one is integrated),
 // folds everything that does not depend on the channel into six constants
 //     dtau = D + P e0 + Q e1 ,  theomax = Th + R e0 + S e1       (e0, e1: profile at the two nodes)
-// and then walks its channels, three at a time: independent dependency chains, no per-channel state but
-// the intensity.  The case split of transfer.F:1517,1542 is a warp vote per group of three channels:
-// all lanes thin (dtau <= 1e-9: about 70 % of all steps in disk atmospheres) -> I <- I (1 - dtau) +
-// theomax, else the branch-free full qdr_src_2 step.  Nodes flagged by the geometry (first segment,
-// inner hole / star mixing, 6q > 1 sub-grid candidates) go through zflagged, out of line.
-// There is no block-level synchronisation: the warps of a block are independent tiles.
+// and then walks its channels: independent dependency chains, no per-channel state but the intensity.
+// The case split of transfer.F:1517,1542 is voted: first for the whole node (D + |P| + |Q| <= 1e-9 on
+// every lane: all channels take I <- I (1 - dtau) + theomax without further tests), else per group of
+// three channels: all lanes thin -> the same update; all lanes dtau > 1e-6 with positive opacities ->
+// qdr_src_2 without its case selections; else the branch-free general step.  Nodes flagged by the
+// geometry (first segment, inner hole / star mixing, 6q > 1 sub-grid candidates) go through zflagged,
+// out of line.  What every lane would otherwise recompute per node (cell offsets, flags, interpolation
+// weight, ds/2, the profile scale) is derived once by the lane that stages the node record.
+// The walk starts at the segment wall_kernel reports (opaque-wall start, below).
+// There is no block-level synchronisation: a block is one warp (kZWarps = 1), 168 registers.
 // ------------------------------------------------------------------------------------------
 constexpr double kIanScale = kTabSqrtScale / 3.33567e-6;  // scaled reciprocal Doppler width per 1/lwav
 
