@@ -306,11 +306,20 @@ __device__ void emit_node(const GeomParams &P, const Ray &R, Emit &E, long long 
 // one thread per node: the record of node i from its LightNode and the one before it on the same ray
 // (whose point values are simply evaluated again: cheaper than a second pass over the records)
 __global__ void __launch_bounds__(256) node_kernel(GeomParams P, long long ntot) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ntot) return;
-  if (i < P.node_off[1]) return;  // the centre ray was finished by geom_kernel (its slots hold no LightNode)
+  // what the next node of the ray needs from this one travels through shared memory (the threads of a
+  // block hold consecutive nodes); only thread 0 evaluates its predecessor a second time
+  __shared__ double s_dvmu[256], s_lw[256], s_s[256];
+  __shared__ int s_ir[256], s_icr[256];
+  const int t = threadIdx.x;
+  const long long i = (long long)blockIdx.x * blockDim.x + t;
+  // (the centre ray was finished by geom_kernel: its slots hold no LightNode)
+  const bool active = i < ntot && i >= P.node_off[1];
   const LightNode *light = static_cast<const LightNode *>(P.light);
-  const LightNode me = light[i];
+  LightNode me;
+  me.s = me.radius = me.theta = 0.0;
+  me.pk = 0;
+  me.iray = 1;
+  if (active) me = light[i];
   const int iray = me.iray;
   const double x0 = P.x0[iray], z0 = P.z0[iray];
   const double costh0 = cos(P.theta0), sinth0 = sin(P.theta0);
@@ -331,23 +340,43 @@ __global__ void __launch_bounds__(256) node_kernel(GeomParams P, long long ntot)
       ir = ir_of_radius(P.g, n.radius);
     }
   };
-  int icr, ir, it;
-  double theta;
-  complete(me, icr, ir, it, theta);
-  const NodePoint pt = node_point(P, x0, z0, costh0, znew, bnew, icr, me.radius, theta, ir, it, me.s);
+  int icr = 0, ir = 0, it = 0;
+  double theta = 0.0;
+  NodePoint pt;
+  pt.dr = pt.dt = pt.lw = pt.dvmu = 0.0;
+  pt.cells = make_int4(0, 0, 0, 0);
+  if (active) {
+    complete(me, icr, ir, it, theta);
+    pt = node_point(P, x0, z0, costh0, znew, bnew, icr, me.radius, theta, ir, it, me.s);
+  }
+  s_dvmu[t] = pt.dvmu;
+  s_lw[t] = pt.lw;
+  s_s[t] = me.s;
+  s_ir[t] = ir;
+  s_icr[t] = icr;
+  __syncthreads();
+  if (!active) return;
   const bool have_prev = i != P.node_off[iray];
   double s_prev = 0.0, dvmu_prev = 0.0, lw_prev = 0.0;
   int ir_old = -99, icr_old = -99;
   if (have_prev) {
-    const LightNode pv = light[i - 1];
-    int it_old;
-    double theta_old;
-    complete(pv, icr_old, ir_old, it_old, theta_old);
-    const NodePoint pp = node_point(P, x0, z0, costh0, znew, bnew, icr_old, pv.radius, theta_old, ir_old, it_old,
-                                    pv.s);
-    s_prev = pv.s;
-    dvmu_prev = pp.dvmu;
-    lw_prev = pp.lw;
+    if (t > 0) {  // node i-1 is on the same ray: thread t-1 evaluated it with the same ray constants
+      s_prev = s_s[t - 1];
+      dvmu_prev = s_dvmu[t - 1];
+      lw_prev = s_lw[t - 1];
+      ir_old = s_ir[t - 1];
+      icr_old = s_icr[t - 1];
+    } else {
+      const LightNode pv = light[i - 1];
+      int it_old;
+      double theta_old;
+      complete(pv, icr_old, ir_old, it_old, theta_old);
+      const NodePoint pp = node_point(P, x0, z0, costh0, znew, bnew, icr_old, pv.radius, theta_old, ir_old,
+                                      it_old, pv.s);
+      s_prev = pv.s;
+      dvmu_prev = pp.dvmu;
+      lw_prev = pp.lw;
+    }
   }
   int star_done = 1;  // (the star is only ever mixed into the centre ray)
   P.nodes.rec[i] = node_record(P, iray, pt, icr, ir, me.s, have_prev, s_prev, ir_old, icr_old, dvmu_prev, lw_prev,
