@@ -17,6 +17,9 @@ Multi-GPU is weak scaling: every rank renders one full 100-line spectrum (lines 
 independent: no data-path collective, only the final gather of the spectra to rank 0).  The
 BASELINE "wall time per 100-line spectrum at N GPUs" (strong scaling, lines block-partitioned like
 radlite.py:1163-1169) is measured in the same run and reported under "strong".
+The library's opaque-wall start is on, as it is for every caller: R (ray-channel
+integrations, the metric's unit) is the reference's count for the workload, the roofline uses the element
+integrations the kernels executed, `roofline.*_reference_work` the reference's element count.
 """
 from __future__ import annotations
 
@@ -322,7 +325,11 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "lines_per_gpu": nl,
                        "l2": "inputs larger than L2: %.2f GB of ray nodes + %.0f MB of per-line cell "
                              "tables per step, geometry rebuilt every step" % (nodes * 60 / 1e9, nl * len(m.r) * len(m.theta) * 32 / 1e6),
-                       "parallelism": f"lines x rays independent; {world} rank(s), one spectrum each"},
+                       "parallelism": f"lines x rays independent; {world} rank(s), one spectrum each",
+                       "opaque_wall": "library default: ray segments behind tau_dust > 150 (seen from the observer) "
+                                      "are not integrated; image bit-identical to the full walk (DESIGN.md 4.3); "
+                                      "value counts the reference's ray-channel integrations, the roofline the "
+                                      "executed element integrations"},
             "element_integrations_per_s": E_tot / dev_s_max,
             "executed_element_fraction": executed / max(1.0, cnt["E"]),
             "wall_ms_per_step": 1e3 * wall_max / args.steps,
