@@ -159,6 +159,10 @@ int rl_max_nodes(const rl_ctx *ctx);
 int rl_get_ray_nodes(rl_ctx *ctx, int iray, double *ds, double *dvmu, double *lw, double *wr,
                      double *wt, int *cells4, int *flags);
 long long rl_total_nodes(const rl_ctx *ctx);
+/* diagnostics: copy a named device buffer of the last render batch to the host ("ztiles", "nstart",
+ * "node_off", "rng", "nitems", "zlines"); returns the bytes the buffer holds (-1: unknown name) and copies
+ * at most nbytes of them */
+long long rl_debug_fetch(rl_ctx *ctx, const char *what, void *out, long long nbytes);
 
 #ifdef __cplusplus
 }

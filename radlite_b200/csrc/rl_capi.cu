@@ -148,6 +148,7 @@ struct rl_ctx {
   double cnt[3] = {0, 0, 0};
   std::vector<double> last_flux;
   int last_nl = 0, last_nfr = 0;
+  long long last_nztile = 0, last_ntask = 0;  // sizes of the last batch's plan (rl_debug_fetch)
 };
 
 #define CU(call)                                                                          \
@@ -191,7 +192,7 @@ int rl_create(rl_ctx **out, int device) {
   if (device < 0 || device >= ndev) return -2;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -3;
-  if (prop.major < 10) return -4;  // built for sm_100a only
+  if (prop.major != 10) return -4;  // the library carries an sm_100a cubin only
   if (cudaSetDevice(device) != cudaSuccess) return -5;
   rl_ctx *c = new rl_ctx();
   c->device = device;
@@ -722,8 +723,11 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
         }
         star[(size_t)l * nfr + k - 1] = sv;
         if (c->out_itype == 3) {  // line.F:3888-3900 (compares with freq_nr = nfr, sic)
+          // the reference's test is j == 0 || j == freq_nr, with freq_nr already confiscated by the passband
+          // (= nfr); it then reads cont_freq_nu(j+1) inside a fixed COMMON array.  Here the bracket must also
+          // lie inside the table (j >= ncf: the line channel is above the last continuum frequency).
           double iv = 0.0;
-          if (!(j == 0 || j == nfr)) {
+          if (!(j == 0 || j == nfr || j >= ncf)) {
             const double w = (fr - cf[j - 1]) / (cf[j] - cf[j - 1]);
             iv = (1.0 - w) * c->isrf_cont[j - 1] + w * c->isrf_cont[j];
           }
@@ -928,6 +932,8 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     CU(c->d_ztiles.ensure(std::max<size_t>(1, total_ctas)));
     P.ztiles = c->d_ztiles.p;
     P.nztile = total_ctas;
+    c->last_nztile = P.use_z ? total_ctas : 0;
+    c->last_ntask = (long long)ntask;
     if (total_ctas) {
       launch_plan(P, true, c->st);
       c->launches++;
@@ -1100,6 +1106,26 @@ int rl_fp64_peak(rl_ctx *c, double *tflops) {
   const double flop = (double)blocks * threads * (double)iters * 16.0 * 2.0;
   *tflops = flop / (best * 1e-3) / 1e12;
   return 0;
+}
+// diagnostics: copy a named device buffer of the last render batch to the host (returns the bytes the buffer
+// holds, copies at most nbytes)
+long long rl_debug_fetch(rl_ctx *c, const char *what, void *out, long long nbytes) {
+  cudaSetDevice(c->device);
+  const void *src = nullptr;
+  long long have = 0;
+  const std::string w(what ? what : "");
+  if (w == "ztiles") { src = c->d_ztiles.p; have = (long long)c->last_nztile * (long long)sizeof(ZTile); }
+  else if (w == "nstart") { src = c->d_nstart.p; have = (long long)c->d_nstart.n * 4; }
+  else if (w == "node_off") { src = c->d_node_off.p; have = ((long long)c->nray + 1) * 8; }
+  else if (w == "rng") { src = c->d_rng.p; have = (long long)c->last_ntask * 16; }
+  else if (w == "nitems") { src = c->d_nitems.p; have = (long long)c->last_ntask * 4; }
+  else if (w == "zlines") { src = c->d_zlines.p; have = (long long)c->last_ntask * 2; }
+  else return -1;
+  if (out && src && nbytes > 0) {
+    cudaMemcpyAsync(out, src, (size_t)std::min(have, nbytes), cudaMemcpyDeviceToHost, c->st);
+    cudaStreamSynchronize(c->st);
+  }
+  return have;
 }
 int rl_max_nodes(const rl_ctx *c) { return c->max_nodes; }
 long long rl_total_nodes(const rl_ctx *c) { return c->total_nodes; }
