@@ -124,6 +124,23 @@ int rl_render_rings(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, d
 int rl_flux_from_rings(rl_ctx *ctx, int nl, int nfr, double dist_cm, const double *ringsum,
                        double *flux);
 
+/* Device-resident variants for sharded renders (one process per GPU): rl_render_rings_device leaves nothing
+ * on the host and copies the ring sums [nl][nrr+1][nfr] into d_ringsum, a DEVICE pointer of the caller (the
+ * buffer the ranks hand to their collective: the blocks are disjoint and the other rows exactly 0, so a sum
+ * reduction is a concatenation); when it returns the buffer is complete (the library's stream is synchronised).
+ * kernel_ms as in rl_render_device (may be NULL).  rl_flux_from_rings_device does the index-ordered ring sum
+ * of telescope.F:1388-1433 on the reduced buffer and returns the spectra to the host.
+ * A ring-block render builds the ray geometry of its own rings only. */
+int rl_render_rings_device(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
+                           int ring_lo, int ring_hi, double *d_ringsum, float *kernel_ms);
+int rl_flux_from_rings_device(rl_ctx *ctx, int nl, int nfr, double dist_cm, const double *d_ringsum,
+                              double *flux);
+/* Work estimate per camera ring [nrr+1] of rendering lines iline0..iline0+nl-1 (geometry, channel selection and
+ * the integrate kernels' node steps; nothing is integrated): the weights for cutting the rings into blocks of
+ * equal work, radlite_b200.shard.split_rings.  The reference's drivers balance by line count only
+ * (radlite.py:1163-1169). */
+int rl_plan_costs(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double *ring_cost);
+
 /* work counters since the last reset: R = ray-channel integrations (charintline calls the
  * reference would make), E = element integrations (integrate_element_linedust calls incl.
  * sub-grid steps), S = ray segments visited. */
@@ -136,6 +153,10 @@ void rl_reset_counters(rl_ctx *ctx);
  * result); 0 integrates every segment.  R, E, S above keep counting the reference's work;
  * rl_get_executed returns the element integrations this library actually performed. */
 int rl_set_wall_tau(rl_ctx *ctx, double tau);
+/* Integrate kernel: 0 = chosen by regime (ztile_kernel + zcont_kernel from 8 lines per batch, tile_kernel
+ * below), 1 = ztile_kernel, 2 = tile_kernel.  The kernels agree to ~1e-13; sharded renders that must be
+ * bit-identical to an unsharded one pin the kernel. */
+int rl_set_kernel(rl_ctx *ctx, int mode);
 double rl_get_executed(const rl_ctx *ctx);
 
 /* ---- device-resident variant used by bench.py's kernel-only timing ----------------------

@@ -17,6 +17,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # RADLITE_B200_LIB selects a tuning variant built by `make variant` (development only)
 LIB_PATH = os.environ.get("RADLITE_B200_LIB") or os.path.join(_HERE, "libradlite_b200.so")
 _lib = None
+# integrate kernel every new Renderer is pinned to: "auto" (library default: by lines per batch), "z", "tile"
+# (the GPU parity tests run every model under all three)
+DEFAULT_KERNEL = "auto"
+_KERNEL_MODES = {"auto": 0, "z": 1, "tile": 2}
 
 
 def load_library() -> C.CDLL:
@@ -63,6 +67,16 @@ class Renderer(Binding):
             raise RuntimeError(
                 f"rl_create(device={device}) failed with {e.code}: no usable sm_100 GPU "
                 "(radlite_b200 has no CPU fallback)") from e
+        self.kernel = "auto"
+        if DEFAULT_KERNEL != "auto":
+            self.set_kernel(DEFAULT_KERNEL)
+
+    def set_kernel(self, mode: str):
+        """Pin the integrate kernel: "auto", "z" (ztile_kernel + zcont_kernel) or "tile" (tile_kernel)."""
+        self.lib.rl_set_kernel.argtypes = [C.c_void_p, C.c_int]
+        self.lib.rl_set_kernel.restype = C.c_int
+        self._check(self.lib.rl_set_kernel(self.ctx, _KERNEL_MODES[mode]))
+        self.kernel = mode
 
     def render_device(self, iline0, nl, nfr, vmax_kms, dist_cm):
         """Kernel-only pass: inputs resident, nothing copied back.  Returns CUDA-event times [ms]

@@ -8,6 +8,7 @@
 #include "rl_types.h"
 
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <cmath>
@@ -19,11 +20,16 @@
 
 namespace rl {
 void launch_geom(const GeomParams &P, bool count, cudaStream_t st);
+void launch_tan2(const GridDev &g, double *tan2, cudaStream_t st);
 void launch_prep(const PrepParams &P, cudaStream_t st);
 void launch_span(const RenderParams &P, cudaStream_t st);
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st);
+void launch_center(const RenderParams &P, cudaStream_t st);
+void launch_zcont(const RenderParams &P, unsigned tile0, unsigned ntile, cudaStream_t st);
+void launch_plan_cost(const RenderParams &P, unsigned n_main, unsigned n_all, double *ring_cost, cudaStream_t st);
 void launch_plan(const RenderParams &P, bool fill, cudaStream_t st);
-void launch_wall(const RenderParams &P, double *admin, int *inverted, int *nstart, cudaStream_t st);
+void launch_wall(const RenderParams &P, double lw_min, double *admin, double *smin, unsigned long long *wstat,
+                 int *nstart, cudaStream_t st);
 int tile_smem_limit(int threads);
 int tile_max_lines(int threads);
 void launch_fill(const RenderParams &P, cudaStream_t st);
@@ -37,6 +43,10 @@ void launch_dfma_peak(double *sink, int iters, int blocks, int threads, cudaStre
 using namespace rl;
 
 namespace {
+
+struct IntToLL {
+  __host__ __device__ long long operator()(int v) const { return (long long)v; }
+};
 
 template <typename T>
 struct DevBuf {
@@ -70,7 +80,10 @@ struct rl_ctx {
   std::string err;
   int device = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;  // side stream: the centre ray and the continuum-only tiles run next to the big kernel
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int kernel_mode = 0;  // 0: by regime, 1: ztile_kernel, 2: tile_kernel (rl_set_kernel)
   long long launches = 0;
   // grid
   int nr = 0, nt = 0, nth = 0;
@@ -114,6 +127,8 @@ struct rl_ctx {
   double levthres = 1e-3, aksmax_opt = -1.0;
   // geometry
   bool geom_valid = false;
+  int geom_ring_lo = 0, geom_ring_hi = 0;  // camera rings the cached node lists cover
+  DevBuf<double> d_tan2;
   long long total_nodes = 0;
   int max_nodes = 0;
   DevBuf<int> d_node_cnt;
@@ -132,13 +147,15 @@ struct rl_ctx {
   DevBuf<CellMask> d_masks;
   DevBuf<TileDesc> d_tiles;
   DevBuf<ZTile> d_ztiles;
-  DevBuf<double> d_admin;   // [ncell] smallest dust opacity of the batch's lines (opaque-wall start)
-  DevBuf<int> d_inverted, d_nstart;
-  double wall_tau = 150.0;  // 0: integrate every segment like the reference does
+  DevBuf<double> d_admin, d_smin;   // [ncell] smallest dust opacity / source function of the batch's lines (opaque-wall start)
+  DevBuf<unsigned long long> d_wstat;  // {largest source function (bit pattern), inverted flag}
+  DevBuf<int> d_nstart;
+  double wall_tau = 64.0;  // e-folds by which the neglected far side lies below the result; 0: integrate every segment like the reference does
   DevBuf<unsigned short> d_zlines;
   DevBuf<unsigned char> d_dense;
   DevBuf<unsigned int> d_nitems, d_item_off, d_ncta, d_cta_off;
   DevBuf<unsigned char> d_scan_tmp;
+  DevBuf<double> d_ring_cost;
   DevBuf<double> d_img, d_ring, d_flux, d_tau;
   DevBuf<unsigned char> d_integ, d_cmask_accum;
   DevBuf<int> d_cmask_out;
@@ -200,10 +217,17 @@ int rl_create(rl_ctx **out, int device) {
     delete c;
     return -6;
   }
+  if (cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaStreamDestroy(c->st);
+    delete c;
+    return -6;
+  }
   for (auto &e : c->ev) cudaEventCreate(&e);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   c->d_status.ensure(1);
-  c->d_counters.ensure(4);
-  cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->st);
+  c->d_counters.ensure(8);
+  cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->st);
   cudaStreamSynchronize(c->st);
   *out = c;
   return 0;
@@ -215,6 +239,10 @@ void rl_destroy(rl_ctx *c) {
   cudaStreamSynchronize(c->st);
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaStreamSynchronize(c->st2);
+  cudaStreamDestroy(c->st2);
   cudaStreamDestroy(c->st);
   delete c;
 }
@@ -553,8 +581,8 @@ static NodesDev nodes_dev(rl_ctx *c) {
   return n;
 }
 
-static int ensure_geometry(rl_ctx *c) {
-  if (c->geom_valid) return 0;
+static int ensure_geometry(rl_ctx *c, int ring_lo, int ring_hi) {
+  if (c->geom_valid && c->geom_ring_lo == ring_lo && c->geom_ring_hi == ring_hi) return 0;
   // telescope.F:4323-4340 telescope_check_safety_numbers
   for (int ir = 1; ir <= c->nr - 1; ir++)
     if (c->rc[ir + 2] / c->rc[ir + 1] - 1.0 < 1.e4 * kTelescEps)
@@ -562,6 +590,9 @@ static int ensure_geometry(rl_ctx *c) {
   GeomParams P;
   P.g = grid_dev(c);
   P.nray = c->nray;
+  // ray 0 = the central beam (ring 0), ring ir = rays 1 + (ir-1) nphi .. ir nphi
+  P.ray_lo = ring_lo <= 0 ? 0 : 1 + (ring_lo - 1) * c->nphi;
+  P.ray_hi = ring_hi <= 0 ? 0 : std::min(c->nray - 1, ring_hi * c->nphi);
   P.x0 = c->d_x0.p;
   P.z0 = c->d_z0.p;
   P.theta0 = c->theta0;
@@ -570,29 +601,37 @@ static int ensure_geometry(rl_ctx *c) {
   P.rbeam0_center = c->imcir_ri[1];
   P.cellS = c->d_cellS.p;
   P.status = c->d_status.p;
-  CU(c->d_node_cnt.ensure(c->nray));
+  CU(c->d_tan2.ensure((size_t)c->nth + 1));
+  launch_tan2(P.g, c->d_tan2.p, c->st);
+  P.tan2 = c->d_tan2.p;
+  CU(c->d_node_cnt.ensure((size_t)c->nray + 1));
   CU(c->d_node_off.ensure((size_t)c->nray + 1));
   CU(cudaMemsetAsync(c->d_status.p, 0, sizeof(int), c->st));
+  CU(cudaMemsetAsync(c->d_node_cnt.p + c->nray, 0, sizeof(int), c->st));
   P.node_cnt = c->d_node_cnt.p;
   P.node_off = nullptr;
   P.nodes = NodesDev{};
   P.light = nullptr;
   P.ntot = 0;
   launch_geom(P, true, c->st);
-  c->launches++;
+  c->launches += 2;
   CU(cudaGetLastError());
-  std::vector<int> cnt(c->nray);
-  CU(cudaMemcpyAsync(cnt.data(), c->d_node_cnt.p, sizeof(int) * c->nray, cudaMemcpyDeviceToHost, c->st));
-  int rcode = check_status(c, "ray geometry, count pass");
-  if (rcode) return rcode;
-  c->h_node_off.assign((size_t)c->nray + 1, 0);
-  c->max_nodes = 0;
-  for (int i = 0; i < c->nray; i++) {
-    c->h_node_off[i + 1] = c->h_node_off[i] + cnt[i];
-    c->max_nodes = std::max(c->max_nodes, cnt[i]);
+  {  // node_off = exclusive scan of the counts (64-bit: 3e8 nodes at BASELINE configs[4])
+    size_t tmp_bytes = 0;
+    auto in = thrust::make_transform_iterator(c->d_node_cnt.p, IntToLL());
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, c->d_node_off.p, c->nray + 1, c->st);
+    CU(c->d_scan_tmp.ensure(tmp_bytes));
+    CU(cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, in, c->d_node_off.p, c->nray + 1, c->st));
+    c->launches++;
   }
-  c->total_nodes = c->h_node_off[c->nray];
-  CU(c->d_node_off.upload(c->h_node_off, c->st));
+  long long total = 0;
+  CU(cudaMemcpyAsync(&total, c->d_node_off.p + c->nray, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+  int rcode = check_status(c, "ray geometry, count pass");  // (synchronises the stream)
+  if (rcode) return rcode;
+  c->total_nodes = total;
+  c->h_node_off.clear();  // fetched on demand (rl_get_ray_nodes)
+  // upper bound of the nodes of one ray (telescope.F:3276, 3198, 3457-3488): sizes the diagnostics' arrays
+  c->max_nodes = 2 * c->nr + c->nt + 34;
   const size_t n = (size_t)c->total_nodes;
   if ((size_t)c->nr * c->nth > (size_t)kCellMask) return fail(c, 13, "grid has too many cells for the node record");
   if (c->nr >= 32768 || c->nt >= 32768) return fail(c, 13, "grid has too many points per axis for the node scratch");
@@ -608,6 +647,8 @@ static int ensure_geometry(rl_ctx *c) {
   rcode = check_status(c, "ray geometry, fill pass");
   if (rcode) return rcode;
   c->geom_valid = true;
+  c->geom_ring_lo = ring_lo;
+  c->geom_ring_hi = ring_hi;
   return 0;
 }
 
@@ -615,7 +656,10 @@ static int ensure_geometry(rl_ctx *c) {
 static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
                        double *flux, double *imcir, int *cmask, double *tau_center, int *maserflag,
                        double *velo_out, float *kernel_ms, bool device_only, int ring_lo = 0,
-                       int ring_hi = 1 << 30, double *ringsum = nullptr) {
+                       int ring_hi = 1 << 30, double *ringsum = nullptr, double *d_ringsum_out = nullptr,
+                       double *ring_cost = nullptr) {
+  // d_ringsum_out: DEVICE pointer that receives the ring sums [nl][nrr+1][nfr] (sharded renders hand them to
+  // the collective without a host round trip); ring_cost: plan only -- per-ring work estimate, no integration
   // telescope.F:366-370, 1511-1515 readiness checks
   if (!c->nr || !c->have_medium || !c->nlines || !(c->have_dust || c->have_line_dust) || !c->cam_set ||
       !c->bc_set)
@@ -637,7 +681,9 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
   cudaSetDevice(c->device);
   float ms_acc[4] = {0, 0, 0, 0};
   CU(cudaEventRecord(c->ev[0], c->st));
-  int rcode = ensure_geometry(c);
+  // a ring-block render builds the node lists of its own rays only (each rank of a sharded render its block)
+  const bool ring_block_geom = ring_lo > 0 || ring_hi < c->nrr;
+  int rcode = ensure_geometry(c, ring_block_geom ? ring_lo : 0, ring_block_geom ? ring_hi : c->nrr);
   if (rcode) return rcode;
   CU(cudaEventRecord(c->ev[1], c->st));
   CU(cudaEventSynchronize(c->ev[1]));
@@ -661,7 +707,9 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
   // tile_kernel: 128-thread blocks when a ray carries enough (line, channel) items, else 64; a tile
   // must hold two slots of all its lines in shared memory twice (double buffer)
   int tile_threads = (lb >= 16) ? 128 : 64;
-  if (const char *e = getenv("RL_TILE_THREADS")) tile_threads = atoi(e) == 64 ? 64 : 128;  // tuning experiments
+#ifdef RL_TUNING_ENV  // development builds only (make variant): environment switches for tuning experiments
+  if (const char *e = getenv("RL_TILE_THREADS")) tile_threads = atoi(e) == 64 ? 64 : 128;
+#endif
   // (the lines a tile spans are bounded by plan_kernel, not by the batch size)
   lb = std::min(lb, kSpanThreads);  // span_kernel: one thread and one mask bit per line
   if (want_mask) {
@@ -777,8 +825,8 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     }
     CU(c->d_nitems.ensure(ntask + 1));
     CU(c->d_item_off.ensure(ntask + 1));
-    CU(c->d_ncta.ensure((size_t)c->nray + 1));
-    CU(c->d_cta_off.ensure((size_t)c->nray + 1));
+    CU(c->d_ncta.ensure(2 * ((size_t)c->nray + 1)));  // ztile plan: general tiles, then continuum-only tiles
+    CU(c->d_cta_off.ensure(2 * ((size_t)c->nray + 1)));
     CU(c->d_img.ensure((size_t)nb * nrow * nfr));
     CU(c->d_ring.ensure((size_t)nb * (c->nrr + 1) * nfr));
     CU(c->d_flux.ensure((size_t)nl * nfr));
@@ -868,14 +916,18 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     // integrate kernel by regime: with several lines per batch the lanes of a warp take lines and share
     // the line-independent profile (ztile_kernel); single-line renders (BASELINE configs 1, 3) spread
     // (line, channel) items over the threads of a block fed by a staging warp (tile_kernel).
-    // RL_KERNEL=z|tile forces one of them (parity tests run both on every model).
+    // rl_set_kernel forces one of them (parity tests run both on every model).
     P.use_z = (nb >= 8 && nfr <= 65535) ? 1 : 0;  // (ZTile carries channel numbers as 16-bit fields)
+    if (c->kernel_mode == 2) P.use_z = 0;
+    else if (c->kernel_mode == 1 && nfr <= 65535) P.use_z = 1;
+    P.zlw = 16;
+#ifdef RL_TUNING_ENV
     if (const char *e = getenv("RL_KERNEL")) {
       if (!strcmp(e, "tile")) P.use_z = 0;
       else if (!strcmp(e, "z") && nfr <= 65535) P.use_z = 1;
     }
-    P.zlw = 16;
     if (const char *e = getenv("RL_ZLW")) P.zlw = atoi(e);
+#endif
     {
       int z = 1;
       while (2 * z <= std::min(32, std::max(1, P.zlw))) z *= 2;
@@ -885,7 +937,9 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.nztile = 0;
     P.nstart = nullptr;
     P.wall_tau = c->wall_tau;
+#ifdef RL_TUNING_ENV
     if (const char *e = getenv("RL_WALL_TAU")) P.wall_tau = atof(e);
+#endif
     CU(c->d_zlines.ensure(ntask));
     P.zlines = c->d_zlines.p;
     P.img = c->d_img.p;
@@ -898,11 +952,14 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     c->launches += P.nonredundant ? 2 : 1;
     if (P.wall_tau > 0.0) {
       CU(c->d_admin.ensure(ncell));
-      CU(c->d_inverted.ensure(1));
+      CU(c->d_smin.ensure(ncell));
+      CU(c->d_wstat.ensure(2));
       CU(c->d_nstart.ensure(c->nray));
-      CU(cudaMemsetAsync(c->d_inverted.p, 0, sizeof(int), c->st));
-      launch_wall(P, c->d_admin.p, c->d_inverted.p, c->d_nstart.p, c->st);
-      c->launches += 2;
+      CU(cudaMemsetAsync(c->d_wstat.p, 0, 2 * sizeof(unsigned long long), c->st));
+      double lw_min = 1.0e300;
+      for (double v : c->h_lw) lw_min = std::min(lw_min, v);
+      launch_wall(P, lw_min, c->d_admin.p, c->d_smin.p, c->d_wstat.p, c->d_nstart.p, c->st);
+      c->launches += 2 + (P.subgrid ? 1 : 0);
       P.nstart = c->d_nstart.p;
     }
     {
@@ -915,34 +972,57 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     }
     launch_plan(P, false, c->st);
     c->launches++;
+    const int nplan = P.use_z ? 2 * (c->nray + 1) : c->nray + 1;
     {
       size_t tmp_bytes = 0;
-      cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_ncta.p, c->d_cta_off.p, c->nray + 1, c->st);
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_ncta.p, c->d_cta_off.p, nplan, c->st);
       CU(c->d_scan_tmp.ensure(tmp_bytes));
-      CU(cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, c->d_ncta.p, c->d_cta_off.p, c->nray + 1,
-                                       c->st));
+      CU(cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, c->d_ncta.p, c->d_cta_off.p, nplan, c->st));
       c->launches++;
     }
-    unsigned total_ctas = 0;
-    CU(cudaMemcpyAsync(&total_ctas, c->d_cta_off.p + c->nray, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+    // tiles of the plan: [0, n_main) for the big kernel, [n_main, n_all) continuum-only (ztile plan only)
+    unsigned tot[2] = {0, 0};
+    CU(cudaMemcpyAsync(&tot[0], c->d_cta_off.p + (P.use_z ? c->nray + 1 : c->nray), sizeof(unsigned),
+                       cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(&tot[1], c->d_cta_off.p + nplan - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
     CU(cudaEventRecord(c->ev[2], c->st));
     CU(cudaStreamSynchronize(c->st));
-    CU(c->d_tiles.ensure(std::max<size_t>(1, total_ctas)));
+    const unsigned n_main = tot[0], n_all = P.use_z ? tot[1] : tot[0];
+    CU(c->d_tiles.ensure(std::max<size_t>(1, P.use_z ? 1 : n_all)));
     P.tiles = c->d_tiles.p;
-    CU(c->d_ztiles.ensure(std::max<size_t>(1, total_ctas)));
+    CU(c->d_ztiles.ensure(std::max<size_t>(1, P.use_z ? n_all : 1)));
     P.ztiles = c->d_ztiles.p;
-    P.nztile = total_ctas;
-    c->last_nztile = P.use_z ? total_ctas : 0;
+    P.nztile = n_main;
+    c->last_nztile = P.use_z ? n_all : 0;
     c->last_ntask = (long long)ntask;
-    if (total_ctas) {
+    if (n_all) {
       launch_plan(P, true, c->st);
       c->launches++;
     }
-    // ---- ray integration ----
-    launch_integrate(P, total_ctas, c->st);
+    if (ring_cost) {  // plan only: work estimate per camera ring (rl_plan_costs), accumulated over the batches
+      CU(c->d_ring_cost.ensure((size_t)c->nrr + 1));
+      if (b0 == 0) CU(cudaMemsetAsync(c->d_ring_cost.p, 0, sizeof(double) * ((size_t)c->nrr + 1), c->st));
+      launch_plan_cost(P, n_main, n_all, c->d_ring_cost.p, c->st);
+      c->launches++;
+      if (b0 + nb >= nl) {
+        CU(cudaMemcpyAsync(ring_cost, c->d_ring_cost.p, sizeof(double) * ((size_t)c->nrr + 1), cudaMemcpyDeviceToHost,
+                           c->st));
+        CU(cudaStreamSynchronize(c->st));
+      }
+      continue;
+    }
+    // ---- ray integration: the big kernel on the main stream; the centre ray and the continuum-only tiles
+    // next to it on the side stream ----
+    CU(cudaEventRecord(c->ev_fork, c->st));
+    CU(cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
+    launch_center(P, c->st2);
+    launch_zcont(P, n_main, n_all - n_main, c->st2);
+    CU(cudaEventRecord(c->ev_join, c->st2));
+    launch_integrate(P, n_main, c->st);
+    CU(cudaStreamWaitEvent(c->st, c->ev_join, 0));
     CU(cudaEventRecord(c->ev[5], c->st));
     launch_fill(P, c->st);
-    c->launches += 2 + (P.nonredundant ? 1 : 0);
+    c->launches += (ring_lo <= 0 ? 1 : 0) + (n_main ? 1 : 0) + (n_all > n_main ? 1 : 0) + (P.nonredundant ? 1 : 0);
     if (imcir) {
       launch_center_replicate(P, c->st);
       c->launches++;
@@ -952,6 +1032,9 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     launch_ringsum(P, c->d_surf.p, c->d_ring.p, c->st);
     launch_flux(nb, c->nrr, nfr, c->d_ring.p, dist_cm * dist_cm, c->d_flux.p + (size_t)b0 * nfr, c->st);
     c->launches += 2;
+    if (d_ringsum_out)
+      CU(cudaMemcpyAsync(d_ringsum_out + (size_t)b0 * (c->nrr + 1) * nfr, c->d_ring.p,
+                         (size_t)nb * (c->nrr + 1) * nfr * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
     if (want_mask) {
       launch_cmask(P, c->d_cmask_accum.p, c->d_cmask_out.p, c->st);
       c->launches++;
@@ -992,10 +1075,12 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[4]));
     ms_acc[3] += ms;
   }
+  if (ring_cost) return 0;
   if (!device_only && flux) {
     CU(cudaMemcpyAsync(flux, c->d_flux.p, (size_t)nl * nfr * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
   }
+  if (d_ringsum_out) CU(cudaStreamSynchronize(c->st));  // the caller's stream may use the buffer now
   if (kernel_ms) {
     for (int i = 0; i < 4; i++) kernel_ms[i] = ms_acc[i];
     CU(cudaEventRecord(c->ev[1], c->st));
@@ -1027,6 +1112,34 @@ int rl_render_rings(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, dou
   std::vector<double> flux((size_t)std::max(nl, 1) * std::max(nfr, 1));
   return render_impl(c, iline0, nl, nfr, vmax_kms, dist_cm, flux.data(), imcir, nullptr, nullptr, nullptr,
                      nullptr, nullptr, false, ring_lo, ring_hi, ringsum);
+}
+
+int rl_render_rings_device(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm, int ring_lo,
+                           int ring_hi, double *d_ringsum, float *kernel_ms) {
+  if (!d_ringsum) return fail(c, 13, "render_rings_device: a device buffer for the ring sums is required");
+  if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
+  return render_impl(c, iline0, nl, nfr, vmax_kms, dist_cm, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     kernel_ms, true, ring_lo, ring_hi, nullptr, d_ringsum);
+}
+
+int rl_flux_from_rings_device(rl_ctx *c, int nl, int nfr, double dist_cm, const double *d_ringsum, double *flux) {
+  if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
+  if (nl < 1 || nfr < 1 || !d_ringsum || !flux) return fail(c, 13, "flux_from_rings_device: bad arguments");
+  cudaSetDevice(c->device);
+  CU(c->d_flux.ensure((size_t)nl * nfr));
+  launch_flux(nl, c->nrr, nfr, d_ringsum, dist_cm * dist_cm, c->d_flux.p, c->st);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(flux, c->d_flux.p, (size_t)nl * nfr * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int rl_plan_costs(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double *ring_cost) {
+  if (!ring_cost) return fail(c, 13, "plan_costs: output array required");
+  if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
+  return render_impl(c, iline0, nl, nfr, vmax_kms, 1.0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     true, 0, 1 << 30, nullptr, nullptr, ring_cost);
 }
 
 int rl_flux_from_rings(rl_ctx *c, int nl, int nfr, double dist_cm, const double *ringsum, double *flux) {
@@ -1072,6 +1185,11 @@ double rl_get_executed(const rl_ctx *cc) {
   cudaStreamSynchronize(c->st);
   return (double)h;
 }
+int rl_set_kernel(rl_ctx *c, int mode) {
+  if (!c || mode < 0 || mode > 2) return 13;
+  c->kernel_mode = mode;
+  return 0;
+}
 int rl_set_wall_tau(rl_ctx *c, double tau) {
   if (!c) return 13;
   c->wall_tau = tau > 0.0 ? tau : 0.0;
@@ -1079,7 +1197,7 @@ int rl_set_wall_tau(rl_ctx *c, double tau) {
 }
 void rl_reset_counters(rl_ctx *c) {
   cudaSetDevice(c->device);
-  cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->st);
+  cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->st);
   cudaStreamSynchronize(c->st);
 }
 
@@ -1116,6 +1234,10 @@ long long rl_debug_fetch(rl_ctx *c, const char *what, void *out, long long nbyte
   const std::string w(what ? what : "");
   if (w == "ztiles") { src = c->d_ztiles.p; have = (long long)c->last_nztile * (long long)sizeof(ZTile); }
   else if (w == "nstart") { src = c->d_nstart.p; have = (long long)c->d_nstart.n * 4; }
+  else if (w == "smin") { src = c->d_smin.p; have = (long long)c->d_smin.n * 8; }
+  else if (w == "admin") { src = c->d_admin.p; have = (long long)c->d_admin.n * 8; }
+  else if (w == "wstat") { src = c->d_wstat.p; have = 16; }
+  else if (w == "counters") { src = c->d_counters.p; have = 64; }
   else if (w == "node_off") { src = c->d_node_off.p; have = ((long long)c->nray + 1) * 8; }
   else if (w == "rng") { src = c->d_rng.p; have = (long long)c->last_ntask * 16; }
   else if (w == "nitems") { src = c->d_nitems.p; have = (long long)c->last_ntask * 4; }
@@ -1137,9 +1259,15 @@ int rl_get_ray_nodes(rl_ctx *c, int iray, double *ds, double *dvmu, double *lw, 
     return -13;
   }
   cudaSetDevice(c->device);
-  int rcode = ensure_geometry(c);
+  int rcode = ensure_geometry(c, 0, c->nrr);
   if (rcode) return -std::abs(rcode);
   if (iray < 1 || iray > c->nray) return -13;
+  if (c->h_node_off.empty()) {
+    c->h_node_off.assign((size_t)c->nray + 1, 0);
+    cudaMemcpyAsync(c->h_node_off.data(), c->d_node_off.p, sizeof(long long) * ((size_t)c->nray + 1),
+                    cudaMemcpyDeviceToHost, c->st);
+    cudaStreamSynchronize(c->st);
+  }
   const long long n0 = c->h_node_off[iray - 1], n = c->h_node_off[iray] - n0;
   std::vector<NodeRec> h((size_t)n);
   cudaMemcpyAsync(h.data(), c->d_nrec.p + n0, (size_t)n * sizeof(NodeRec), cudaMemcpyDeviceToHost, c->st);

@@ -38,6 +38,7 @@ __device__ int hunt_bisect(const double *xx1, int n, double x) {
 
 struct Ray {
   GridDev g;
+  const double *tan2;  // [nt/2 + 1] tan^2 of the cone angles (index iy = 1..nt/2)
   double x0, z0, costh0, sinth0, costh02, sinth02, pitheta0;
   // theta-crossing stream
   int isnr, isdbl, iy_first, iup, branchA, ith_amount;
@@ -48,9 +49,7 @@ struct Ray {
 
 // both roots of the theta=const cone iy (telescope.F:2960-2990), ordered sar1 <= sar2
 __device__ bool th_roots(const Ray &R, int iy, double &sar1, double &sar2) {
-  double theta = TCf(R.g, iy);
-  double t = tan(theta);
-  double tanth2 = t * t;
+  double tanth2 = R.tan2[iy];  // tan(theta_iy)^2, tabulated once per grid by tan2_kernel
   double a = tanth2 * R.costh02 - R.sinth02;
   double b = 2.0 * tanth2 * R.costh0 * R.z0;
   double c = tanth2 * R.z0 * R.z0 - R.x0 * R.x0;
@@ -383,14 +382,27 @@ __global__ void __launch_bounds__(256) node_kernel(GeomParams P, long long ntot)
                                star_done);
 }
 
+// tan(theta_iy)^2 of the stored hemisphere's cones (telescope.F:2960-2962 evaluates it per ray and cone)
+__global__ void tan2_kernel(GridDev g, double *tan2) {
+  const int iy = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iy < 1 || iy > g.nt / 2) return;
+  const double t = tan(TCf(g, iy));
+  tan2[iy] = t * t;
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
   const int iray = blockIdx.x * blockDim.x + threadIdx.x;
   if (iray >= P.nray) return;
   const GridDev &g = P.g;
   const int nr = g.nr, nt = g.nt;
+  if (iray < P.ray_lo || iray > P.ray_hi) {  // a ray of another rank's ring block
+    if (COUNT) P.node_cnt[iray] = 0;
+    return;
+  }
   Ray R;
   R.g = g;
+  R.tan2 = P.tan2;
   R.x0 = P.x0[iray];
   R.z0 = P.z0[iray];
   R.rstar = P.rstar;
@@ -553,7 +565,7 @@ __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
   const long long base = COUNT ? 0 : P.node_off[iray];
   // rays finished by node_kernel: the bracketing searches of a node (theta cell of an R crossing, radial
   // cell of a theta crossing) are left to it as well -- they are the expensive serial part of the merge
-  const bool lazy = !COUNT && iray != 0;
+  const bool lazy = COUNT || iray != 0;
   Emit E;
   E.n = 0;
   E.ir_old = -99;
@@ -613,6 +625,10 @@ __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
 }
 
 }  // namespace
+
+void launch_tan2(const GridDev &g, double *tan2, cudaStream_t st) {
+  tan2_kernel<<<(g.nt / 2 + 1 + 127) / 128, 128, 0, st>>>(g, tan2);
+}
 
 void launch_geom(const GeomParams &P, bool count, cudaStream_t st) {
   const int threads = 128;

@@ -601,6 +601,31 @@ __device__ __forceinline__ void full_step(double &inten, double alp0, double r0,
   inten = fma(inten, x, qv);
 }
 
+// The same step with ONE division: a S_a + b S_b (a = e0 - b, b = e1 / dtau on the thick branch, a = b = dtau / 2
+// on the thin one; S = j / alpha of the node itself or, where its opacity is not positive, of the other node:
+// transfer.F:1517-1541) brought over the common denominator.  Used by ztile_kernel and zcont_kernel for every
+// step that is not all-thin; a lane with dtau > 1e-6 and both opacities positive performs exactly the
+// operations of ztile_kernel's select-free variant, so its result does not depend on which of the two the
+// warp's vote picks.
+constexpr double kAlpMin = 1.0e-150;  // alpha <= this is treated like alpha <= 0 (the product of two opacities and
+                                      // dtau must stay a normal number)
+__device__ __forceinline__ void step_onediv(double alp0, double src0, double alp1, double src1, double dtau,
+                                            double theomax, uint32_t T1, double &x, double &qv) {
+  const double xpe = expneg_tab(dtau, T1, 0);
+  const double e0 = 1.0 - xpe, e1 = dtau - e0;
+  const bool thick = dtau > 1.e-6;
+  const bool p0 = alp0 > kAlpMin, p1 = alp1 > kAlpMin;
+  const double nA = p0 ? src0 : (p1 ? src1 : 0.0), dA = p0 ? alp0 : (p1 ? alp1 : 1.0);
+  const double nB = p1 ? src1 : (p0 ? src0 : 0.0), dB = p1 ? alp1 : (p0 ? alp0 : 1.0);
+  const double hb = 0.5 * dtau;
+  const double ca = thick ? fma(e0, dtau, -e1) : hb, cb = thick ? e1 : hb, dd = thick ? dtau : 1.0;
+  const double den = dd * (dA * dB);
+  const double num = fma(ca, nA * dB, cb * (nB * dA));
+  x = thick ? xpe : (1.0 - dtau);
+  qv = div_fast(num, den);
+  qv = (dtau > (double)1e-9f) ? fmin(qv, theomax) : theomax;
+}
+
 // sub-gridded segment in the staged (cN, kk) form (line.F:4745-4833); reference-ordered arithmetic
 __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch, double &inten, double ds,
                                          double sleft, double sright, double sd0, double ad0, double cN0,
@@ -1299,6 +1324,9 @@ __device__ __noinline__ unsigned zflagged(double *Ic, const ZSeg &g, uint32_t fl
 #ifndef RL_ZSTREAM
 #define RL_ZSTREAM 1
 #endif
+#ifndef RL_ZONEDIV
+#define RL_ZONEDIV 1
+#endif
 #ifndef RL_ZMINB
 #define RL_ZMINB 6  // resident blocks per SM the register budget is set for (6: 168 registers, no hot-loop spills)
 #endif
@@ -1517,10 +1545,20 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
 #pragma unroll
                 for (int k = 0; k < 3; k++) I[cb + k] = fma(I[cb + k], 1.0 - dtau[k], theo[k]);
               } else {
+#ifdef RL_STATS
+                {
+                  const double em = fmax(fmax(fmax(ep[0], ec[0]), fmax(ep[1], ec[1])), fmax(ep[2], ec[2]));
+                  const bool far = !__any_sync(0xffffffffu, em > 8.0e-28);
+                  if (lane == 0) {
+                    atomicAdd(&P.counters[4], 1ull);
+                    if (far) atomicAdd(&P.counters[5], 1ull);
+                  }
+                }
+#endif
                 const double K0 = v0.kk * nrm0, A0 = v0.cN * nrm0, K1 = v1.kk * nrm1, A1 = v1.cN * nrm1;
 #if RL_ZSTREAM
                 // lanes whose dust opacity alone is positive never see alpha <= 0 unless the line inverts
-                const bool odd = neg | thin_some | !(v0.ad > kAlpTiny) | !(v1.ad > kAlpTiny) | (v0.kk < 0.0);
+                const bool odd = neg | thin_some | !(v0.ad > kAlpMin) | !(v1.ad > kAlpMin) | (v0.kk < 0.0);
                 if (!__any_sync(0xffffffffu, odd)) {
                   // every lane: dtau > 1e-6 and both opacities positive -- qdr_src_2 without its case
                   // selections (the operations of step_coeffs on this branch, bit for bit)
@@ -1528,11 +1566,20 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
                   for (int k = 0; k < 3; k++) {
                     const double alp1 = fma(K1, ec[k], v1.ad), src1 = fma(A1, ec[k], v1.sd);
                     const double alp0 = fma(K0, ep[k], v0.ad), src0 = fma(A0, ep[k], v0.sd);
-                    const double r0 = div_fast(src0, alp0), r1 = div_fast(src1, alp1);
                     const double xpe = expneg_tab(dtau[k], T1, 0);
+#if RL_ZONEDIV
+                    // a S0 + b S1 with a = e0 - b, b = e1 / dtau, S = j / alpha (transfer.F:1519-1541) over the
+                    // common denominator dtau alp0 alp1: one reciprocal instead of three
+                    const double e0 = 1.0 - xpe, e1 = dtau[k] - e0;
+                    const double den = dtau[k] * (alp0 * alp1);
+                    const double num = fma(fma(e0, dtau[k], -e1), src0 * alp1, e1 * (src1 * alp0));
+                    const double qv = fmin(div_fast(num, den), theo[k]);
+#else
+                    const double r0 = div_fast(src0, alp0), r1 = div_fast(src1, alp1);
                     const double e0 = 1.0 - xpe;
                     const double bt = div_fast(dtau[k] - e0, dtau[k]);
                     const double qv = fmin(fma(e0 - bt, r0, bt * r1), theo[k]);
+#endif
                     I[cb + k] = fma(I[cb + k], xpe, qv);
                   }
                 } else
@@ -1542,9 +1589,14 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
                   for (int k = 0; k < 3; k++) {
                     const double alp1 = fma(K1, ec[k], v1.ad), src1 = fma(A1, ec[k], v1.sd);
                     const double alp0 = fma(K0, ep[k], v0.ad), src0 = fma(A0, ep[k], v0.sd);
+                    double x, q;
+#if RL_ZONEDIV
+                    step_onediv(alp0, src0, alp1, src1, dtau[k], theo[k], T1, x, q);
+#else
                     const double r0 = div_fast(src0, alp0);
-                    double r1, x, q;
+                    double r1;
                     step_coeffs(alp0, r0, src1, alp1, r1, dtau[k], theo[k], T1, x, q);
+#endif
                     I[cb + k] = fma(I[cb + k], x, q);
                     if (neg && (K1 * ec[k]) * nd->ds < (double)(-0.01f)) mbits |= 1u << (cb + k);  // telescope.F:4295
                   }
@@ -1611,6 +1663,245 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// zcont_kernel: the (ray, line) pairs that carry no channel window on a ray -- the reference integrates
+// only their first channel (telescope.F:544-554), whose intensity then stands for all others.  They are a
+// quarter of all ray x node steps of a multi-line render but 4 % of its element integrations, and running
+// them through ztile_kernel (nine channel slots per thread, 168 registers) wastes both.  Here one warp
+// = one ray x 32 such lines (one per lane) x channel 0, four independent warps per block, few registers:
+// many resident warps hide the gather latency, and two unflagged segments are evaluated per iteration with
+// their loads and their dependency chains interleaved.
+// The profile at channel 0 does not depend on the line (see ztile_kernel): one lane per node evaluates it
+// while staging the node record.  Where it is exactly 0 at a node (the rule far from the line centre: it is
+// flushed below exp(-345)) the line terms of that node vanish identically -- x + 0 y = x -- so only the
+// dust pair {j_d, alpha_d} of the cell records is gathered (needfull = 0).
+// Arithmetic per lane is that of ztile_kernel's general step (same functions), so a (ray, line) pair gives
+// the same bits whichever kernel integrates it.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) ZCNode {
+  uint32_t offA, offB, offC, offD;  // element offsets (cell * nl) of the stencil cells in cellL (C, D: extra points)
+  double w, w2;                     // weight between A and B (and C, D) ; between the pairs (extra points)
+  double hds, inv_lwav;             // ds / 2 ; reciprocal mean width of the segment ending here
+  double lw, dvmu;                  // node values the flagged path needs (line.F:4706-4715)
+  double ian, e;                    // profile scale of that segment ; profile value at channel 0
+  uint32_t fl, icr, needfull, pad;  // segment flags ; crossing type ; line terms needed at this node
+};
+constexpr int kZcWarps = 4;
+
+__global__ void __launch_bounds__(32 * kZcWarps, 6) zcont_kernel(const __grid_constant__ RenderParams P, unsigned tile0,
+                                                                 unsigned ntile) {
+  __shared__ ZCNode s_zc[kZcWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < kTabN) s_T1[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kTabN));
+  __syncthreads();
+  const unsigned tix = blockIdx.x * kZcWarps + warp;
+  if (tix >= ntile) return;
+  const ZTile t = P.ztiles[tile0 + tix];
+  const int ray = t.ray;
+  const bool lineok = lane < (int)t.nlt;
+  const int l = (int)P.zlines[t.loff + (lineok ? lane : 0)];
+  const LineDev *Lp = P.lines + l;
+  const double c_src = __ldg(&Lp->c_src);
+  const double cb_du = __ldg(&Lp->c_alp) * __ldg(&Lp->bdu), cb_ud = __ldg(&Lp->c_alp) * __ldg(&Lp->bud);
+  const double knorm = 0.56419583546 / __ldg(&Lp->k_aa);
+  const long long n0 = P.node_off[ray];
+  const int N = (int)(P.node_off[ray + 1] - n0);
+  const int ns = P.nstart ? max(1, min(__ldg(&P.nstart[ray]), N - 1)) : 1;
+  double I = ns > 1 ? 0.0 : ((P.out_itype == 3) ? __ldg(&P.isrf_line[(size_t)l * P.nfr]) : __ldg(&Lp->i_outer));
+  const NodeRec *__restrict__ rec = P.nodes.rec + n0;
+  const double4 *__restrict__ cl = P.cellL + l;
+  const uint32_t nl = (uint32_t)P.nl;
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
+  ZCNode *sn = s_zc[warp];
+  const double vel0 = __ldg(P.velz);
+  constexpr long long kThin = 0x3E112E0BE0000000LL;  // bit pattern of (double)1e-9f (transfer.F:1542, REAL literal)
+  unsigned mbits = 0, xtra = 0;
+
+  // interpolated cell values of this lane's line at a staged node: all four fields, or the dust pair only
+  auto full_at = [&](const ZCNode *x) {
+    const double4 a = ldg4(cl + x->offA), b = ldg4(cl + x->offB);
+    if (x->icr == 3) return zvals(interp4(a, b, ldg4(cl + x->offC), ldg4(cl + x->offD), x->w2, x->w), c_src, cb_du, cb_ud);
+    return zvals(interp2(a, b, x->w), c_src, cb_du, cb_ud);
+  };
+  auto dust2 = [&](const ZCNode *x, double2 a, double2 b) {
+    const double w = x->w, w1 = 1.0 - w;
+    return make_double2(lerp_rn(a.x, b.x, w, w1), lerp_rn(a.y, b.y, w, w1));
+  };
+  auto dust_at = [&](const ZCNode *x) {
+    ZVal o;
+    o.cN = o.kk = 0.0;
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(cl + x->offA));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(cl + x->offB));
+    double2 r;
+    if (x->icr == 3) {
+      const double2 c = __ldg(reinterpret_cast<const double2 *>(cl + x->offC));
+      const double2 d = __ldg(reinterpret_cast<const double2 *>(cl + x->offD));
+      const double t1 = 1.0 - x->w, r1 = 1.0 - x->w2;
+      r.x = lerp_rn(lerp_rn(a.x, b.x, x->w, t1), lerp_rn(c.x, d.x, x->w, t1), x->w2, r1);
+      r.y = lerp_rn(lerp_rn(a.y, b.y, x->w, t1), lerp_rn(c.y, d.y, x->w, t1), x->w2, r1);
+    } else {
+      r = dust2(x, a, b);
+    }
+    o.sd = r.x;
+    o.ad = r.y;
+    return o;
+  };
+  // one unflagged segment with the line terms (the arithmetic of zstep/ztile_kernel's grouped path)
+  auto seg_full = [&](const ZVal &v0, const ZVal &v1, double nrm0, double nrm1, const ZCNode *x, double ep, double ec) {
+    const double hds = x->hds;
+    const double hn0 = hds * nrm0, hn1 = hds * nrm1;
+    const double D = hds * (v0.ad + v1.ad), Th = hds * (v0.sd + v1.sd);
+    const double Pq = hn0 * v0.kk, Q = hn1 * v1.kk, R = hn0 * v0.cN, S = hn1 * v1.cN;
+    const bool neg = v1.kk < 0.0;
+    const double dtau = fma(Pq, ep, fma(Q, ec, D)), theo = fma(R, ep, fma(S, ec, Th));
+    const bool work = neg | (__double_as_longlong(dtau) > kThin);
+    if (!__any_sync(0xffffffffu, work)) {
+      I = fma(I, 1.0 - dtau, theo);
+    } else {
+      const double K0 = v0.kk * nrm0, A0 = v0.cN * nrm0, K1 = v1.kk * nrm1, A1 = v1.cN * nrm1;
+      const double alp1 = fma(K1, ec, v1.ad), src1 = fma(A1, ec, v1.sd);
+      const double alp0 = fma(K0, ep, v0.ad), src0 = fma(A0, ep, v0.sd);
+      double xx, q;
+      step_onediv(alp0, src0, alp1, src1, dtau, theo, T1, xx, q);
+      I = fma(I, xx, q);
+      if (neg && (K1 * ec) * (hds + hds) < (double)(-0.01f)) mbits |= 1u;  // telescope.F:4295
+    }
+  };
+
+  ZVal v0;
+  v0.sd = v0.ad = v0.cN = v0.kk = 0.0;
+  double nrm0 = 0.0;
+  for (int c0 = ns; c0 < N; c0 += 30) {
+    const int cnt = min(30, N - c0);
+    __syncwarp();  // the previous batch is consumed
+    {  // stage nodes c0-1 .. c0+cnt (the last one only as look-ahead for needfull) -> rows 0 .. cnt+1
+      const int nstage = min(cnt + 2, N - (c0 - 1));
+      uint32_t fl = 0;
+      double e = 0.0;
+      ZCNode x;
+      if (lane < nstage) {
+        const int node = c0 - 1 + lane;
+        const double2 *p = reinterpret_cast<const double2 *>(rec + node);
+        const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        const int4 cells = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        x.icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
+        x.offA = (uint32_t)(cells.x & kCellMask) * nl;
+        x.offB = (uint32_t)(x.icr == 2 ? cells.z : cells.y) * nl;
+        x.offC = (uint32_t)cells.z * nl;
+        x.offD = (uint32_t)cells.w * nl;
+        fl = ((uint32_t)cells.x >> kCellFlagShift) & ~kFlagIcrMask;
+        if (!P.subgrid) fl &= ~kFlagSub;
+        if (node == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
+        if (node == 0) fl = 0;           // (the first node ends no segment)
+        x.fl = fl;
+        x.w = x.icr == 2 ? c.x : c.y;  // wr : wt
+        x.w2 = c.x;
+        x.hds = 0.5 * a.x;
+        x.inv_lwav = b.y;
+        x.lw = b.x;
+        x.dvmu = a.y;
+        x.ian = b.y * kIanScale;
+        e = gauss_tab(fma(vel0, x.ian, -(a.y * x.ian)), T1, 0);
+        x.e = e;
+        x.pad = 0;
+      }
+      // the line terms of a node enter through its own profile value -- as the end point of its segment
+      // (which a flag sends to zflagged with both end points in full) and as the start point of the next
+      // segment, where the carried state multiplies this same value (line.F:4613-4615) unless that
+      // segment is flagged too
+      const uint32_t fl_next = __shfl_down_sync(0xffffffffu, fl, 1);
+      const bool last = lane + 1 >= nstage;
+      x.needfull = (e != 0.0 || fl != 0 || (last ? 1u : fl_next) != 0) ? 1u : 0u;
+      if (lane < nstage) sn[lane] = x;
+    }
+    __syncwarp();
+    if (c0 == ns) {  // values at the node the first integrated segment starts from
+      v0 = sn[0].needfull ? full_at(sn) : dust_at(sn);
+      nrm0 = knorm * sn[0].inv_lwav;
+    }
+    int s = 1;
+    while (s <= cnt) {
+      const ZCNode *x1 = sn + s;
+      if (s < cnt && (x1->fl | x1->needfull | x1[1].fl | x1[1].needfull | x1[-1].needfull) == 0 &&
+          (x1->icr != 3) && (x1[1].icr != 3)) {
+        // two dust-only segments at once (nodes s-1, s, s+1 carry no line terms)
+        const ZCNode *x2 = x1 + 1;
+        const double2 a1 = __ldg(reinterpret_cast<const double2 *>(cl + x1->offA));
+        const double2 b1 = __ldg(reinterpret_cast<const double2 *>(cl + x1->offB));
+        const double2 a2 = __ldg(reinterpret_cast<const double2 *>(cl + x2->offA));
+        const double2 b2 = __ldg(reinterpret_cast<const double2 *>(cl + x2->offB));
+        const double2 d1 = dust2(x1, a1, b1), d2 = dust2(x2, a2, b2);
+        const double h1 = x1->hds, h2 = x2->hds;
+        const double D1 = h1 * (v0.ad + d1.y), T1h = h1 * (v0.sd + d1.x);
+        const double D2 = h2 * (d1.y + d2.y), T2h = h2 * (d1.x + d2.x);
+        const bool work = (__double_as_longlong(D1) > kThin) | (__double_as_longlong(D2) > kThin);
+        if (!__any_sync(0xffffffffu, work)) {
+          I = fma(fma(I, 1.0 - D1, T1h), 1.0 - D2, T2h);
+        } else {
+          double xa, qa, xb, qb;
+          step_onediv(v0.ad, v0.sd, d1.y, d1.x, D1, T1h, T1, xa, qa);
+          step_onediv(d1.y, d1.x, d2.y, d2.x, D2, T2h, T1, xb, qb);
+          I = fma(fma(I, xa, qa), xb, qb);
+        }
+        v0.sd = d2.x;
+        v0.ad = d2.y;
+        v0.cN = v0.kk = 0.0;
+        nrm0 = knorm * x2->inv_lwav;
+        s += 2;
+        continue;
+      }
+      const ZVal v1 = x1->needfull ? full_at(x1) : dust_at(x1);
+      const double nrm1 = knorm * x1->inv_lwav;
+      if (x1->fl == 0) {
+        seg_full(v0, v1, nrm0, nrm1, x1, x1[-1].e, x1->e);
+      } else {
+        double tmp[1] = {I};
+        ZSeg sg;
+        sg.ds = x1->hds + x1->hds;
+        sg.lwav = 0.5 * (x1[-1].lw + x1->lw);
+        sg.dv0 = x1[-1].dvmu;
+        sg.dv1 = x1->dvmu;
+        sg.ian = x1->ian;
+        sg.nrm0 = nrm0;
+        sg.nrm1 = nrm1;
+        sg.v0 = v0;
+        sg.v1 = v1;
+        const uint32_t ep_a = (uint32_t)__cvta_generic_to_shared(&x1[-1].e);
+        const uint32_t ec_a = (uint32_t)__cvta_generic_to_shared(&x1->e);
+        mbits |= zflagged(tmp, sg, x1->fl, 1, ep_a, ec_a, Lp, P.line_dnu + (size_t)l * P.nfr,
+                          P.star_line + (size_t)l * P.nfr, P.velz, 0, 1, 0, 1, P.starfract, lineok ? 1u : 0u, xtra);
+        I = tmp[0];
+      }
+      v0 = v1;
+      nrm0 = nrm1;
+      s++;
+    }
+  }
+  unsigned long long r = 0;
+  if (lineok) {
+    const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
+    P.img[row * P.nfr] = I;
+    if (P.sparse && I == 0.0) P.dense[(long long)ray * P.nl + l] = 2;  // see fill_sparse_kernel
+    if (P.integ) P.integ[row * P.nfr] = 1;  // channel 0 is always a masked one (telescope.F:548)
+    if (mbits) atomicOr(&P.maser[l], 1);
+    r = 1;
+  }
+  unsigned long long sct = r * (unsigned long long)(N > 0 ? N - 1 : 0), e = sct + (lineok ? xtra : 0u);
+  unsigned long long ex = r * (unsigned long long)(N > ns ? N - ns : 0) + (lineok ? xtra : 0u);
+  for (int o = 16; o; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    sct += __shfl_xor_sync(0xffffffffu, sct, o);
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  if (lane == 0 && r) {
+    atomicAdd(&P.counters[0], r);
+    atomicAdd(&P.counters[1], e);
+    atomicAdd(&P.counters[2], sct);
+    atomicAdd(&P.counters[3], ex);
+  }
+}
+
 // tiles of ztile_kernel, one thread per ray.  The lines that carry a channel window on this ray (in index
 // order, compacted into zlines) are cut into groups of zlw; the channel list of a group is
 // {0} + [min lo, max hi] over its lines (a superset of every line's own item channels -- the kernel
@@ -1621,13 +1912,14 @@ template <bool FILL>
 __global__ void zplan_kernel(RenderParams P) {
   const int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray > P.nray) return;
-  unsigned n = 0;
+  unsigned n = 0, ncont = 0;
   if (ray < P.nray) {
     const int4 *rg = P.rng + (size_t)ray * P.nl;
     const unsigned *ni = P.nitems + (size_t)ray * P.nl;
     unsigned short *zl = P.zlines + (size_t)ray * P.nl;
     ZTile *out = FILL ? P.ztiles + P.cta_off[ray] : nullptr;
-    auto emit = [&](int start, int cnt, int cmin, int cmax) {
+    ZTile *outc = FILL ? P.ztiles + P.cta_off[P.nray + 1 + ray] : nullptr;
+    auto emit = [&](int start, int cnt, int cmin, int cmax, bool cont) {
       if (cmax < cmin) { cmin = 1; cmax = 0; }
       const int nch = 1 + (cmax - cmin + 1);
       int lws = 0;
@@ -1644,82 +1936,140 @@ __global__ void zplan_kernel(RenderParams P) {
           t.nchk = (unsigned short)min(per, nch - j0);
           t.nlt = (unsigned char)cnt;
           t.lwshift = (unsigned char)lws;
-          out[n] = t;
+          if (cont) outc[ncont] = t;
+          else out[n] = t;
         }
-        n++;
+        if (cont) ncont++;
+        else n++;
       }
     };
     int na = 0;
-    for (int pass = 0; pass < 2; pass++) {  // 0: lines with a channel window, 1: the others
+    // pass 0: lines with a channel window; pass 1: lines that need channel 0 only (zcont_kernel's tiles);
+    // pass 2: lines without a window whose channel 0 lies inside the ray's velocity span, so that their
+    // first skipped channel is integrated as well (telescope.F:557-612; rare)
+    for (int pass = 0; pass < 3; pass++) {
       const int gsz = pass ? 32 : P.zlw;
       int gstart = na, cmin = 0x7fffffff, cmax = -1;
       for (int l = 0; l < P.nl; l++) {
         if (!ni[l]) continue;
         const int4 r = rg[l];
-        if ((r.y < r.x) != (pass == 1)) continue;
+        const int cls = (r.y >= r.x) ? 0 : (r.z < 0 ? 1 : 2);
+        if (cls != pass) continue;
         if (FILL) zl[na] = (unsigned short)l;
         if (r.y >= r.x) { cmin = min(cmin, r.x); cmax = max(cmax, r.y); }
         if (r.z >= 0) { cmin = min(cmin, r.z); cmax = max(cmax, r.z); }
         na++;
         if (na - gstart == gsz) {
-          emit(gstart, gsz, cmin, cmax);
+          emit(gstart, gsz, cmin, cmax, pass == 1);
           gstart = na; cmin = 0x7fffffff; cmax = -1;
         }
       }
-      if (na > gstart) emit(gstart, na - gstart, cmin, cmax);
+      if (na > gstart) emit(gstart, na - gstart, cmin, cmax, pass == 1);
     }
   }
-  if (!FILL) P.ncta[ray] = n;
+  if (!FILL) {
+    P.ncta[ray] = n;
+    P.ncta[P.nray + 1 + ray] = ncont;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
-// Opaque-wall start.  Whatever a ray has accumulated before it enters an optically thick dust layer is
-// multiplied by exp(-tau) on the way out: with tau > wall_tau = 150 that is a relative contribution below
-// 1e-65, forty-nine orders of magnitude below the rounding of the result, so the segments in front of
-// the wall (seen from the far end of the ray) need not be integrated.  The bound is line independent and
-// conservative: admin[cell] = the smallest dust opacity any line of the batch has in the cell, interpolated
-// with the node's own weights (all in [0, 1]: a lower bound of every line's interpolated opacity), summed
-// from the observer's end of the ray; line opacity only adds to it (batches with an inverted level pair
-// anywhere are not shortened at all).  The reference integrates those segments (telescope.F:4079-4300 has
-// no such cut); its work counters R, S are reported unchanged, the executed element integrations separately.
+// Opaque-wall start.  What a ray has accumulated before it enters an optically thick dust layer leaves that
+// layer multiplied by exp(-tau); once that is far below the rounding of what the layer itself emits towards
+// the observer, the segments behind it need not be integrated.  wall_kernel finds, per ray and for all lines
+// of the batch at once, the first segment n from which on this provably holds:
+//   dropped  <=  Smax exp(-tau_n)          Smax: the largest source function of any cell and line of the batch
+//                                          (and the outer boundary intensity); qdr_src_2 never raises the
+//                                          intensity above max(I, S1, S2) (transfer.F:1498-1571, a + b = 1 - xp)
+//   kept     >=  Smin_n (1 - exp(-tau_n))  Smin_n: the smallest source function, over lines and over the line
+//                                          profile (0 .. its peak value), of the cells the nodes n-1 .. N-1
+//                                          interpolate from; every step adds at least (1 - xp) min(S1, S2)
+//   tau_n    =   dust optical depth of segments n .. N-1, from the smallest dust opacity any line of the batch
+//                has in a cell, interpolated with the nodes' own weights (all in [0, 1]); line opacity only adds
+// and cuts where  tau_n - ln(Smax / Smin_n) > wall_tau  (default 64: the neglected part is below e^-64 ~ 1e-28
+// of the result).  A batch with an inverted level pair or a negative dust opacity anywhere is never shortened,
+// and a ray whose front crosses a cell without emission (T_dust = 0, or no dust at all) keeps its full
+// length: Smin = 0 there.  The reference integrates every segment (telescope.F:4079-4300 has no such cut); its
+// work counters R, E, S are reported unchanged (wallcount_kernel adds the sub-grid steps of the skipped
+// segments), the executed element integrations separately.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) wallprep_kernel(RenderParams P, double *admin, int *inverted) {
+__device__ __forceinline__ void atomic_max_pos(double *addr, double v) {  // v >= 0: bit patterns order like values
+  atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+// wstat: {Smax (bit pattern of a non-negative double), inverted flag}
+__global__ void __launch_bounds__(256) wallprep_kernel(RenderParams P, double lw_min, double *admin, double *smin,
+                                                       unsigned long long *wstat) {
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= P.ncell) return;
-  double mn = 1.0e300;
+  double mn = 1.0e300, lo = 1.0e300, hi = 0.0;
   bool inv = false;
   for (int l = 0; l < P.nl; l++) {
     const double4 v = ldg4(P.cellL + (size_t)cell * P.nl + l);
+    const LineDev *L = P.lines + l;
     mn = fmin(mn, v.y);
-    inv = inv || (v.w * __ldg(&P.lines[l].bdu) - v.z * __ldg(&P.lines[l].bud) < 0.0) || !(v.y >= 0.0);
+    const double kk = __ldg(&L->c_alp) * (v.w * __ldg(&L->bdu) - v.z * __ldg(&L->bud));
+    const double cN = __ldg(&L->c_src) * v.z;
+    inv = inv || (kk < 0.0) || !(v.y >= 0.0) || !(v.x >= 0.0);
+    // source function over the profile range 0 .. phimax: monotone in phi, so its extremes sit at the ends
+    const double phimax = 0.56419583546 / (__ldg(&L->k_aa) * lw_min);
+    const double s0 = v.y > 0.0 ? v.x / v.y : (v.x > 0.0 ? 1.0e300 : 0.0);
+    const double a1 = v.y + kk * phimax;
+    const double s1 = a1 > 0.0 ? (v.x + cN * phimax) / a1 : s0;
+    lo = fmin(lo, v.y > 0.0 ? fmin(s0, s1) : 0.0);  // a cell without dust opacity gives no bound
+    hi = fmax(hi, fmax(s0, s1));
+    if (cell == 0) {  // outer boundary intensity of the line (telescope.F:3989-4028)
+      double ib = __ldg(&L->i_outer);
+      if (P.out_itype == 3)
+        for (int k = 0; k < P.nfr; k++) ib = fmax(ib, __ldg(&P.isrf_line[(size_t)l * P.nfr + k]));
+      hi = fmax(hi, ib);
+    }
   }
   admin[cell] = mn;
-  if (inv) atomicOr(inverted, 1);
+  smin[cell] = lo;
+  if (!(hi >= 0.0) || hi > 1.0e300) hi = 1.0e300;
+  atomic_max_pos(reinterpret_cast<double *>(&wstat[0]), hi);
+  if (inv) atomicOr(&wstat[1], 1ull);
 }
 
 __global__ void __launch_bounds__(128) wall_kernel(RenderParams P, const double *__restrict__ admin,
-                                                   const int *__restrict__ inverted, int *nstart) {
+                                                   const double *__restrict__ smin,
+                                                   const unsigned long long *__restrict__ wstat, int *nstart) {
   const int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= P.nray) return;
   int ns = 1;
   const long long n0 = P.node_off[ray];
   const int N = (int)(P.node_off[ray + 1] - n0);
-  if (ray > 0 && N > 2 && P.wall_tau > 0.0 && !__ldg(inverted)) {
+  const double smax = __longlong_as_double((long long)__ldg(&wstat[0]));
+  if (ray > 0 && N > 2 && P.wall_tau > 0.0 && !__ldg(&wstat[1]) && smax < 1.0e299) {
     const NodeRec *rec = P.nodes.rec + n0;
-    auto amin_at = [&](int n) {
+    const double lsmax = smax > 0.0 ? log(smax) : -1.0e300;
+    // lower bounds at a node: dust opacity (interpolated) and source function (smallest of the stencil cells)
+    auto at = [&](int n, double &amin, double &sm) {
       const Node nd = load_node(P.nodes.rec, n0 + n);
       const int icr = nd.flags & kFlagIcrMask;
       const double a = __ldg(&admin[nd.cells.x]);
-      if (icr == 1) return (1.0 - nd.wt) * a + nd.wt * __ldg(&admin[nd.cells.y]);
-      if (icr == 2) return (1.0 - nd.wr) * a + nd.wr * __ldg(&admin[nd.cells.z]);
-      return (1.0 - nd.wr) * ((1.0 - nd.wt) * a + nd.wt * __ldg(&admin[nd.cells.y])) +
-             nd.wr * ((1.0 - nd.wt) * __ldg(&admin[nd.cells.z]) + nd.wt * __ldg(&admin[nd.cells.w]));
+      sm = __ldg(&smin[nd.cells.x]);
+      if (icr == 1) {
+        amin = (1.0 - nd.wt) * a + nd.wt * __ldg(&admin[nd.cells.y]);
+        sm = fmin(sm, __ldg(&smin[nd.cells.y]));
+      } else if (icr == 2) {
+        amin = (1.0 - nd.wr) * a + nd.wr * __ldg(&admin[nd.cells.z]);
+        sm = fmin(sm, __ldg(&smin[nd.cells.z]));
+      } else {
+        amin = (1.0 - nd.wr) * ((1.0 - nd.wt) * a + nd.wt * __ldg(&admin[nd.cells.y])) +
+               nd.wr * ((1.0 - nd.wt) * __ldg(&admin[nd.cells.z]) + nd.wt * __ldg(&admin[nd.cells.w]));
+        sm = fmin(fmin(sm, __ldg(&smin[nd.cells.y])), fmin(__ldg(&smin[nd.cells.z]), __ldg(&smin[nd.cells.w])));
+      }
     };
-    double cum = 0.0, a1 = amin_at(N - 1);
+    double cum = 0.0, a1, sfront;
+    at(N - 1, a1, sfront);
     for (int n = N - 1; n >= 2; n--) {  // segment n joins nodes n-1 and n
-      const double a0 = amin_at(n - 1);
+      double a0, s0;
+      at(n - 1, a0, s0);
+      sfront = fmin(sfront, s0);
       cum += 0.5 * __ldg(&rec[n].ds) * (a0 + a1);
-      if (cum > P.wall_tau) {
+      if (!(sfront > 0.0)) break;  // no emission bound in front: the ray keeps its full length
+      if (cum > P.wall_tau && cum - (lsmax - log(sfront)) > P.wall_tau) {
         ns = n;
         break;
       }
@@ -1727,6 +2077,89 @@ __global__ void __launch_bounds__(128) wall_kernel(RenderParams P, const double 
     }
   }
   nstart[ray] = ns;
+}
+
+// The element integrations of the sub-gridded segments that the opaque-wall start skips, added to the E
+// counter so that it stays the reference's count (line.F:4745-4833: a sub-gridded segment takes one
+// integration per sub-point strictly inside it plus one).  One block per ray: threads first act as channels
+// (the number of sub-points is a function of segment and channel alone -- the velocity grid is the same for
+// every line), then as lines (sum over the channels the reference integrates for that line).
+__global__ void __launch_bounds__(128) wallcount_kernel(RenderParams P, const int *__restrict__ nstart, int tile_shift) {
+  extern __shared__ unsigned s_x[];  // [nfr + 1] extra integrations per channel, then their prefix sums
+  const int ray = blockIdx.x;
+  const long long n0 = P.node_off[ray];
+  const int N = (int)(P.node_off[ray + 1] - n0);
+  int first = max(1, min(nstart[ray], N - 1));             // first segment ztile_kernel / zcont_kernel integrate
+  if (tile_shift) first = max(0, min(nstart[ray], N - 1) - 2) + 1;  // tile_kernel starts one segment earlier
+  if (first <= 1 || !P.subgrid) return;
+  for (int ch = threadIdx.x; ch < P.nfr; ch += blockDim.x) {
+    const double vel = __ldg(&P.velz[ch]);
+    unsigned cnt = 0;
+    Node p = load_node(P.nodes.rec, n0);
+    for (int n = 1; n < first; n++) {
+      const Node c = load_node(P.nodes.rec, n0 + n);
+      if (c.flags & kFlagSub) {
+        const double ds = c.ds, lwav = 0.5 * (p.lw + c.lw);
+        const double q = fabs((c.dvmu - p.dvmu) / (lwav / 2.99792458e5));
+        const double s_c = ds * (vel - p.dvmu) / (c.dvmu - p.dvmu);
+        const double dls3 = 3.0 * (ds / q);
+        const double sright = s_c + dls3, sleft = s_c - dls3;
+        if (sright > 0.0 && sleft < ds) {
+          const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
+          for (int j = 1; j <= kLgNrMax; j++) {
+            const double sj = sleft + (j - 1) * lg_ds;
+            if (sj > 0.0 && sj < ds) cnt++;
+          }
+        }
+      }
+      p = c;
+    }
+    s_x[ch] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // exclusive prefix over channels 1..nfr-1 (s_x[0] stays the count of channel 0)
+    unsigned run = 0;
+    for (int ch = 1; ch < P.nfr; ch++) {
+      const unsigned v = s_x[ch];
+      s_x[ch] = run;
+      run += v;
+    }
+    s_x[P.nfr] = run;
+  }
+  __syncthreads();
+  unsigned long long e = 0;
+  for (int l = threadIdx.x; l < P.nl; l += blockDim.x) {
+    const long long task = (long long)ray * P.nl + l;
+    if (!P.nitems[task]) continue;
+    const int4 rg = P.rng[task];
+    e += s_x[0];
+    if (rg.y >= rg.x) e += s_x[rg.y + 1] - s_x[rg.x];
+    if (rg.z >= 1) e += s_x[rg.z + 1] - s_x[rg.z];
+  }
+  for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if ((threadIdx.x & 31) == 0 && e) atomicAdd(&P.counters[1], e);
+}
+
+// Work estimate of a plan per camera ring (rl_plan_costs: cost-weighted ring blocks for sharded renders), in
+// units of warp instructions as the profiles show them: a ztile_kernel node step costs about 120 + 40 per
+// channel slot of the thread, a zcont_kernel one about 100; building and scanning a ray's nodes (geometry,
+// channel selection, wall) about 170 per node.
+__global__ void __launch_bounds__(256) plan_cost_kernel(RenderParams P, unsigned n_main, unsigned n_all, double *cost) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_all) {
+    const ZTile t = P.ztiles[i];
+    const int N = (int)(P.node_off[t.ray + 1] - P.node_off[t.ray]);
+    const int ns = P.nstart ? max(1, min(P.nstart[t.ray], N - 1)) : 1;
+    const int GW = 32 >> t.lwshift, cw = (t.nchk + GW - 1) / GW, cw3 = 3 * ((cw + 2) / 3);
+    const double per = i < n_main ? 120.0 + 40.0 * cw3 : 100.0;
+    const int ring = t.ray == 0 ? 0 : 1 + (t.ray - 1) / P.nphi;
+    atomicAdd(&cost[ring], per * (double)max(0, N - ns));
+  }
+  if (i < (unsigned)P.nray) {
+    const int N = (int)(P.node_off[i + 1] - P.node_off[i]);
+    const int ring = i == 0 ? 0 : 1 + ((int)i - 1) / P.nphi;
+    atomicAdd(&cost[ring], 170.0 * (double)N + (i == 0 ? 400.0 * (double)N * P.nl * P.nfr / 32.0 : 0.0));
+  }
 }
 
 // the centre ray (telescope.F:498-527): one thread per (line, channel), reference-ordered scalar
@@ -1932,13 +2365,23 @@ __global__ void __launch_bounds__(128) ringsum_kernel(RenderParams P, const doub
   } else {
     // skipped channels carry the row's continuum (telescope.F:582-612), never written in this mode
     long long task = ((long long)(1 + (ir - 1) * P.nphi)) * P.nl + l;
-    for (int ip = 0; ip < P.nphi; ip++, task += P.nl) {
-      const int4 rg = __ldg(&P.rng[task]);
+    auto pixel = [&](int ip, long long tk) {
+      const int4 rg = __ldg(&P.rng[tk]);
       const double *row = I - c + (size_t)ip * P.nfr;
-      const bool own = (c == 0) || (c >= rg.x && c <= rg.y) || (c == rg.z) || P.dense[task];
+      const bool own = (c == 0) || (c >= rg.x && c <= rg.y) || (c == rg.z) || P.dense[tk];
       const int src = own ? c : ((rg.w == 0) ? 0 : rg.z);
-      dslum = dslum + row[src];
+      return row[src];
+    };
+    int ip = 0;
+    for (; ip + 4 <= P.nphi; ip += 4, task += 4 * (long long)P.nl) {  // four pixels in flight, summed in index order
+      const double v0 = pixel(ip, task), v1 = pixel(ip + 1, task + P.nl), v2 = pixel(ip + 2, task + 2 * (long long)P.nl),
+                   v3 = pixel(ip + 3, task + 3 * (long long)P.nl);
+      dslum = dslum + v0;
+      dslum = dslum + v1;
+      dslum = dslum + v2;
+      dslum = dslum + v3;
     }
+    for (; ip < P.nphi; ip++, task += P.nl) dslum = dslum + pixel(ip, task);
   }
   dslum = dslum / (1.0 * P.nphi);
   dslum = dslum * surf[ir];
@@ -1999,9 +2442,12 @@ void launch_span(const RenderParams &P, cudaStream_t st) {
   if (P.nonredundant) mask_kernel<<<(unsigned)((P.ncell * 4 + 255) / 256), 256, 0, st>>>(P);
   span_kernel<<<(unsigned)P.nray, kSpanThreads, 0, st>>>(P);
 }
-void launch_wall(const RenderParams &P, double *admin, int *inverted, int *nstart, cudaStream_t st) {
-  wallprep_kernel<<<(unsigned)((P.ncell + 255) / 256), 256, 0, st>>>(P, admin, inverted);
-  wall_kernel<<<(P.nray + 127) / 128, 128, 0, st>>>(P, admin, inverted, nstart);
+void launch_wall(const RenderParams &P, double lw_min, double *admin, double *smin, unsigned long long *wstat,
+                 int *nstart, cudaStream_t st) {
+  wallprep_kernel<<<(unsigned)((P.ncell + 255) / 256), 256, 0, st>>>(P, lw_min, admin, smin, wstat);
+  wall_kernel<<<(P.nray + 127) / 128, 128, 0, st>>>(P, admin, smin, wstat, nstart);
+  if (P.subgrid)
+    wallcount_kernel<<<P.nray, 128, (P.nfr + 1) * sizeof(unsigned), st>>>(P, nstart, P.use_z ? 0 : 1);
 }
 void launch_plan(const RenderParams &P, bool fill, cudaStream_t st) {
   if (P.use_z) {
@@ -2030,8 +2476,18 @@ int tile_max_lines(int threads) {
   // 3 slots of (kPairBytes nlc + kSlotBytes) + phantom (sizeof(HotLine) nlc + sizeof(HotNode))
   return min(kMaxTileLines, (per_buf - 3 * kSlotBytes - (int)sizeof(HotNode)) / (3 * kPairBytes + (int)sizeof(HotLine)));
 }
-void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
+void launch_plan_cost(const RenderParams &P, unsigned n_main, unsigned n_all, double *ring_cost, cudaStream_t st) {
+  const unsigned n = max(n_all, (unsigned)P.nray);
+  plan_cost_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, n_main, n_all, ring_cost);
+}
+void launch_center(const RenderParams &P, cudaStream_t st) {
   if (P.ring_lo <= 0) center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);
+}
+// the continuum-only tiles [tile0, tile0 + ntile) of the ztile plan
+void launch_zcont(const RenderParams &P, unsigned tile0, unsigned ntile, cudaStream_t st) {
+  if (ntile) zcont_kernel<<<(ntile + kZcWarps - 1) / kZcWarps, 32 * kZcWarps, 0, st>>>(P, tile0, ntile);
+}
+void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
   if (!total_ctas) return;
   if (P.use_z) {
     ztile_kernel<kZCw><<<(total_ctas + kZWarps - 1) / kZWarps, 32 * kZWarps, 0, st>>>(P);

@@ -82,6 +82,8 @@ struct NodesDev {
 struct GeomParams {
   GridDev g;
   int nray;
+  int ray_lo, ray_hi;  // rays built by this call (a camera-ring block); the others get no nodes
+  const double *tan2;  // [nt/2 + 1] tan^2 of the cone angles
   const double *x0;  // [nray]
   const double *z0;
   double theta0;
@@ -128,7 +130,10 @@ struct __align__(16) ZTile {
   unsigned short cmin, j0, nchk;
   unsigned char nlt, lwshift;
 };
-constexpr int kZCw = 9;         // channels per ztile_kernel thread (three groups of three)
+#ifndef RL_ZCW
+#define RL_ZCW 9
+#endif
+constexpr int kZCw = RL_ZCW;         // channels per ztile_kernel thread (three groups of three)
 constexpr int kZTab = 1024;     // profile-table entries per warp
 #ifndef RL_ZWARPS
 #define RL_ZWARPS 1

@@ -240,8 +240,8 @@ def make_model(name, nr, nth, mol, *, incl_deg=15.0, vmax_kms=70.0, dv_kms=1.5, 
               lev_v=mol["lev_v"], lev_j=mol["lev_j"], lev_up=mol["lev_up"],
               lev_down=mol["lev_down"], aud=mol["aud"], linefreq=mol["linefreq"], popul=popul,
               nsize=np.array([1], dtype=np.int32), cont_freq_nu=cf, kappa_abs=kabs,
-              kappa_scat=kscat, dust_rho=np.ascontiguousarray(rho_d[..., None]),
-              dust_temp=np.ascontiguousarray(tgas[..., None, None]), scati_src=None,
+              kappa_scat=kscat, dust_rho=np.array(rho_d[..., None], order="C"),
+              dust_temp=np.array(tgas[..., None, None], order="C"), scati_src=None,
               rstar=rstar, mstar=mstar, tstar=tstar, starspec_cont=planck(cf, tstar),
               incl_deg=incl_deg, nphi=nphi, nrext=nrext, dbdr=dbdr, vmax_kms=vmax_kms,
               dv_kms=dv_kms, out_itype=out_itype)

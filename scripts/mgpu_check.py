@@ -1,7 +1,7 @@
 """Multi-GPU check (run under torchrun, one rank per GPU): line-block and ring-block sharded renders
 over NCCL must be bit-identical to the single-GPU render.  The library picks its integrate kernel by the
 number of lines per batch (ztile_kernel from 8, tile_kernel below; they differ at the 1e-13 level), so the
-check pins one kernel at a time (RL_KERNEL=z, then tile) for the bitwise comparison and then verifies the
+check pins one kernel at a time (rl_set_kernel: z, then tile) for the bitwise comparison and then verifies the
 library's own choice to 1e-10.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/mgpu_check.py"""
 import os
@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from radlite_b200 import shard, synth  # noqa: E402
+from radlite_b200 import api, shard, synth  # noqa: E402
 from radlite_b200.api import Renderer  # noqa: E402
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
@@ -20,9 +20,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 for kern in ("z", "tile", ""):
-  os.environ.pop("RL_KERNEL", None)
-  if kern:
-    os.environ["RL_KERNEL"] = kern
+  api.DEFAULT_KERNEL = kern or "auto"
   same = np.array_equal if kern else (lambda a, b: np.allclose(a, b, rtol=1e-10, atol=0.0))
   m = synth.config(2, nr=60, nth=24, nphi=24, nrext=-12, nlines=11)
   g = Renderer(local)

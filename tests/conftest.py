@@ -27,10 +27,11 @@ def renderer_cls():
 
 def same_bits(a, b):
     """Spectra of one line rendered in different batches / subsets: bit-identical when one integrate
-    kernel serves both renders (RL_KERNEL forced), 1e-10 when the library picks the kernel by lines per
+    kernel serves both renders (api.DEFAULT_KERNEL pinned), 1e-10 when the library picks the kernel by lines per
     batch (tile_kernel below 8 lines, ztile_kernel from 8: they round differently at the 1e-13 level)."""
     import numpy as np
-    if os.environ.get("RL_KERNEL") in ("z", "tile"):
+    from radlite_b200 import api
+    if api.DEFAULT_KERNEL in ("z", "tile"):
         return np.array_equal(a, b)
     return np.allclose(a, b, rtol=1e-10, atol=0.0)
 
@@ -38,10 +39,8 @@ def same_bits(a, b):
 @pytest.fixture(params=["auto", "z", "tile"])
 def integrate_kernel(request):
     """Runs a GPU test once per integrate kernel (library default by regime, ztile_kernel, tile_kernel)."""
-    old = os.environ.pop("RL_KERNEL", None)
-    if request.param != "auto":
-        os.environ["RL_KERNEL"] = request.param
+    from radlite_b200 import api
+    old = api.DEFAULT_KERNEL
+    api.DEFAULT_KERNEL = request.param
     yield request.param
-    os.environ.pop("RL_KERNEL", None)
-    if old is not None:
-        os.environ["RL_KERNEL"] = old
+    api.DEFAULT_KERNEL = old

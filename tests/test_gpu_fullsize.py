@@ -15,14 +15,11 @@ pytestmark = pytest.mark.gpu
 def _kernel(request):
     """Each full-size test once with the library's kernel choice and once with ztile_kernel forced
     (tile_kernel at these sizes is covered by the configs it serves: the single-line ones)."""
-    import os
-    old = os.environ.pop("RL_KERNEL", None)
-    if request.param != "auto":
-        os.environ["RL_KERNEL"] = request.param
+    from radlite_b200 import api
+    old = api.DEFAULT_KERNEL
+    api.DEFAULT_KERNEL = request.param
     yield
-    os.environ.pop("RL_KERNEL", None)
-    if old is not None:
-        os.environ["RL_KERNEL"] = old
+    api.DEFAULT_KERNEL = old
 TOL_PIX = 1e-5
 
 
@@ -46,6 +43,43 @@ def flux_from_cube(g, img, dist):
     f = 3.14159265359 * ri[1] ** 2 * img[0, 0]
     f = f + (img[1:].mean(axis=1) * surf[:nrr, None]).sum(axis=0)
     return f / dist**2
+
+
+def test_cfg2_100_lines_as_benchmarked(renderer_cls, oracle_cls):
+    """configs[1] exactly as bench.py renders it -- all 100 lines in ONE batch (7 tiles of 16 lines per ray
+    plus the continuum-only tiles), spectrum mode for the flux, cube + mask for the pixel checks -- against
+    the oracle on three camera rings: every pixel and mask value of those rings for lines 1, 16, 17 (a tile
+    boundary), 50 and 100, and the ray-channel / segment / element counts of the rings for all 100 lines."""
+    m = synth.config(2)
+    assert (m.nlines, m.nray, m.nfr) == (100, 40351, 94)
+    nl, nfr = m.nlines, m.nfr
+    g = renderer_cls(0)
+    g.load_model(m)
+    flux = g.render(1, nl, nfr, m.passband, synth.PARSEC)["flux"]  # what bench.py's e2e leg returns
+    out = g.render(1, nl, nfr, m.passband, synth.PARSEC, want_image=True, want_mask=True)
+    assert np.array_equal(out["flux"], flux)
+    o = oracle_cls()
+    o.load_model(m)
+    lines = [1, 16, 17, 50, 100]
+    for ir in (75, 150, 262):
+        o.reset_counters()
+        o.set_ring_sample(ir, ir, 1)
+        ref = o.render(1, nl, nfr, m.passband, synth.PARSEC, want_image=True, want_mask=True)
+        co = o.counters()
+        for il in lines:
+            assert rel_err(out["image"][il - 1, ir], ref["image"][il - 1, ir]).max() < TOL_PIX, (ir, il)
+            assert rel_err(out["image"][il - 1, 0], ref["image"][il - 1, 0]).max() < TOL_PIX, (ir, il)
+        # imcir_cmask accumulates over the lines of a run in both (telescope.F:548,575 never clear it)
+        assert np.array_equal(out["cmask"][:, ir], ref["cmask"][:, ir]), ir
+        # the reference's work for this ring (+ the centre ray, which the oracle always traces)
+        g.reset_counters()
+        g.render_rings(1, nl, nfr, m.passband, synth.PARSEC, ir, ir)
+        g.render_rings(1, nl, nfr, m.passband, synth.PARSEC, 0, 0)
+        cg = g.counters()
+        assert cg["R"] == co["R"] and cg["S"] == co["S"], (ir, cg, co)
+        assert abs(cg["E"] - co["E"]) <= 1e-6 * co["E"], (ir, cg, co)
+        del ref
+    o.set_ring_sample(0, 0, 1)
 
 
 def test_cfg3_13co_cube_full_size(renderer_cls, oracle_cls):

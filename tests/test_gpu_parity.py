@@ -43,12 +43,10 @@ def check(g, out, o, ref, image=True, counters=True):
     if counters:
         cg, co = g.counters(), o.counters()
         assert cg["R"] == co["R"] and cg["S"] == co["S"]
-        # E: a sub-grid point on a segment end may flip (1e-6); with the opaque-wall start (default on for
-        # ztile_kernel) the extra elements of sub-gridded segments behind a wall are not counted -- the
-        # exact comparison with the wall off is in test_opaque_wall_start_is_exact
-        assert cg["E"] <= co["E"] * (1 + 1e-6) and cg["E"] >= cg["S"]
-        if g.executed_elements() == cg["E"]:  # nothing was skipped
-            assert abs(cg["E"] - co["E"]) <= 1e-6 * co["E"]
+        # E: a sub-grid point on a segment end may flip (1e-6).  The opaque-wall start (on by default) does not
+        # change the counter: wallcount_kernel adds the sub-grid steps of the segments it skips
+        assert abs(cg["E"] - co["E"]) <= 1e-6 * co["E"] and cg["E"] >= cg["S"]
+        assert g.executed_elements() <= cg["E"]
 
 
 @pytest.mark.parametrize("name,model", list(golden_cases()), ids=[n for n, _ in golden_cases()])
@@ -127,7 +125,11 @@ def test_maser_flag(renderer_cls, oracle_cls):
     m.abund[:] = 1e-3
     g, out, o, ref = both(renderer_cls, oracle_cls, m)
     assert ref["maserflag"][0] == 1 and out["maserflag"][0] == 1
-    assert rel_err(out["flux"], ref["flux"]).max() < 1e-4
+    # under inversion qdr_src_2 takes its a = b = dtau/2, xp = 1 - dtau, Q = theomax branch (transfer.F:1522-1524,
+    # 1545) with dtau < 0: the amplification compounds along the ray, and so does the 1e-13 difference between
+    # the kernels' and the reference's exp / division -- still inside the per-channel tolerance
+    assert rel_err(out["flux"], ref["flux"]).max() < TOL_CH
+    assert rel_err(out["image"], ref["image"]).max() < TOL_PIX
 
 
 def test_precomputed_line_dust_and_line_subsets(renderer_cls, oracle_cls):
@@ -254,7 +256,7 @@ def test_cfg2_full_size_properties(renderer_cls, oracle_cls):
     frac_on = g.executed_elements() / g.counters()["E"]
     g.set_wall_tau(0.0)
     assert np.array_equal(g.render(1, 8, m.nfr, m.passband, synth.PARSEC)["flux"], f)
-    g.set_wall_tau(150.0)
+    g.set_wall_tau(64.0)
     assert 0.3 < frac_on < 0.9, frac_on  # about 40 % of this disk's element integrations lie behind walls
     # rendering lines one by one gives bit-identical spectra (lines are independent)
     one = g.render(5, 1, m.nfr, m.passband, synth.PARSEC)
@@ -272,9 +274,9 @@ def test_cfg2_full_size_properties(renderer_cls, oracle_cls):
 
 
 def test_opaque_wall_start_is_exact(renderer_cls, oracle_cls, integrate_kernel):
-    """rl_set_wall_tau: segments behind tau_dust > 150 are not integrated by ztile_kernel; the image must not
-    change in any bit (their contribution is attenuated by exp(-150)), the reference's work counters R, S
-    stay what they are and only the executed element count drops."""
+    """rl_set_wall_tau: segments whose contribution is provably below e^-64 of what the dust in front of them
+    emits are not integrated; the image must not change in any bit, the reference's work counters R, E, S stay
+    what they are and only the executed element count drops."""
     m = synth.config(2, nr=60, nth=24, nphi=16, nrext=-8, nlines=8)
     g = renderer_cls(0)
     g.load_model(m)
@@ -292,7 +294,7 @@ def test_opaque_wall_start_is_exact(renderer_cls, oracle_cls, integrate_kernel):
     assert c_off["R"] == co["R"] and c_off["S"] == co["S"] and abs(c_off["E"] - co["E"]) <= 1e-6 * co["E"]
     assert np.array_equal(on["flux"], off["flux"])
     assert np.array_equal(on["image"], off["image"])
-    assert c_on["R"] == c_off["R"] and c_on["S"] == c_off["S"] and c_on["E"] <= c_off["E"]
+    assert c_on["R"] == c_off["R"] and c_on["S"] == c_off["S"] and c_on["E"] == c_off["E"]
     assert ex_off == c_off["E"]
     assert ex_on < 0.9 * ex_off, (ex_on, ex_off)  # this disk's midplane is opaque at 4.7 um
     g.set_wall_tau(1.0)  # an absurdly thin "wall": now the image must change (the cut really is applied)
