@@ -1,25 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- RADLite line ray-tracing hot path on N B200s of one node.
 
-Metric (BASELINE.json): ray-channel integrations/s on the CO fundamental 100-line LTE spectrum
-(configs[1]: 200x80 (r,theta) grid, 40 351 camera rays, 94 velocity channels per line).  A "ray-
-channel integration" is one call the reference makes to charintline (telescope.F:3889), i.e. one
-ray traced at one velocity channel of one line; both arms count the same units (R).
+Metric (BASELINE.json): ray-channel integrations/s -- and the wall time of ONE spectrum at 1/2/4/8 GPUs.  A
+"ray-channel integration" is one call the reference makes to charintline (telescope.F:3889), i.e. one ray
+traced at one velocity channel of one line; both arms count the same units (R).  The workload is
+configs[1] unless --config says otherwise: the CO fundamental 100-line LTE spectrum on the 200x80 (r,theta)
+grid, 40 351 camera rays, 94 velocity channels per line.
 
-  python bench.py --gpus 1 --steps K --warmup W          # this repo's CUDA path
-  python bench.py --impl reference --steps K --warmup W  # CPU restatement of the reference
-  torchrun ... bench.py --gpus N ...                      # one rank per GPU, lines are sharded
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path, one GPU
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference
+  torchrun ... bench.py --gpus N ...                        # one rank per GPU: ONE spectrum over N GPUs
+  python bench.py --config {1,3,4,5}                       # the other BASELINE configs (5: a 64-line slice)
 
-A step = one pass of the hot path over one batch = ray geometry + all lines of the rank's
-spectrum.  `value` times it with every input resident in HBM (rl_render_device); `e2e` times
-rl_set_* + rl_render through the C ABI from host buffers to the host flux array.
-Multi-GPU is weak scaling: every rank renders one full 100-line spectrum (lines and rays are
-independent: no data-path collective, only the final gather of the spectra to rank 0).  The
-BASELINE "wall time per 100-line spectrum at N GPUs" (strong scaling, lines block-partitioned like
-radlite.py:1163-1169) is measured in the same run and reported under "strong".
-The library's opaque-wall start is on, as it is for every caller: R (ray-channel
-integrations, the metric's unit) is the reference's count for the workload, the roofline uses the element
-integrations the kernels executed, `roofline.*_reference_work` the reference's element count.
+A step = one pass of the hot path over one batch = ray geometry + all lines of the spectrum.
+N = 1:  `value` times it with every input resident in HBM (rl_render_device); `e2e` times rl_set_* + rl_render
+        through the C ABI from host buffers to the host flux array (cube for the cube config).
+N > 1:  strong scaling -- the SAME spectrum, camera rings cut into N blocks of equal estimated work
+        (rl_plan_costs), every rank builds the geometry of its own rays and integrates all lines on them
+        (rl_render_rings_device); the one exchange is a sum reduction of the ring sums (disjoint rows: a
+        concatenation) over NCCL to rank 0, which does the reference's index-ordered ring sum.  The result
+        is compared bit for bit with the one-GPU render.  `replicas` additionally reports N independent
+        spectra (weak scaling, no exchange).
+The library's opaque-wall start is on, as it is for every caller: R and E are the reference's
+counts for the workload; the roofline uses the element integrations the kernels executed.
 """
 from __future__ import annotations
 
@@ -42,12 +45,33 @@ from radlite_b200 import synth  # noqa: E402
 METRIC = "ray-channel integrations/s"
 UNIT = "ray-channel integrations/s"
 FLOP_PER_ELEMENT = 64.0  # FP64 flop per element integration, exp excluded
-WORKLOAD = ("configs[1]: CO fundamental 100-line LTE spectrum, 200x80 (r,theta) grid, nphi=150, "
-            "b_extra=-60, 40351 rays, 94 channels (70 km/s @ 1.5 km/s), incl 15 deg, spectrum mode")
+
+# BASELINE.json configs: model keyword overrides, what is rendered, label
+CONFIGS = {
+    1: dict(kw={}, cube=False,
+            label="configs[0]: single CO v=1-0 P(10) line, LTE, 100x40 (r,theta) grid, 25351 rays, 94 channels, "
+                  "incl 15 deg, spectrum mode"),
+    2: dict(kw={}, cube=False,
+            label="configs[1]: CO fundamental 100-line LTE spectrum, 200x80 (r,theta) grid, nphi=150, "
+                  "b_extra=-60, 40351 rays, 94 channels (70 km/s @ 1.5 km/s), incl 15 deg, spectrum mode"),
+    3: dict(kw={}, cube=True,
+            label="configs[2]: 13CO image cube (circular-polar pixels, 199 velocity channels), 400x160 grid, "
+                  "70351 rays, incl 45 deg, cube mode"),
+    4: dict(kw={}, cube=False,
+            label="configs[3]: 12CO two-temperature (NLTE stand-in) populations, every 4.6-5.0 um line of "
+                  "v<=9, J<=60 (442 lines, 4 batches), 200x80 grid, dust continuum, spectrum mode"),
+    5: dict(kw=dict(nlines=64), cube=False,
+            label="configs[4]: 1000x400 grid, line widths x0.2 (velocity sub-gridding on most segments), "
+                  "160351 rays; a 64-line slice of the 2000 synthetic lines (per-line cost is the same), "
+                  "spectrum mode"),
+}
 
 
-def model_for_bench(nlines=100):
-    return synth.config(2, nlines=nlines)
+def model_for_bench(cfg=2, nlines=None):
+    kw = dict(CONFIGS[cfg]["kw"])
+    if nlines:
+        kw["nlines"] = nlines
+    return synth.config(cfg, **kw)
 
 
 def input_arrays(m):
@@ -59,10 +83,20 @@ def input_arrays(m):
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle (C restatement of the reference; the Fortran binary cannot be built here)
 # ------------------------------------------------------------------------------------------
+def _oracle_flags():
+    try:
+        for ln in open(os.path.join(ROOT, "oracle", "Makefile")):
+            if ln.startswith("CFLAGS"):
+                return "gcc " + ln.split("=", 1)[1].strip()
+    except OSError:
+        pass
+    return "gcc (flags unknown)"
+
+
 def _cpu_worker(args):
-    iline, ring_stride, nlines = args
+    cfg, iline, ring_stride, nlines = args
     from oracle.oracle_py import Oracle
-    m = model_for_bench(nlines)
+    m = model_for_bench(cfg, nlines)
     o = Oracle()
     o.load_model(m)
     if ring_stride > 1:
@@ -74,17 +108,22 @@ def _cpu_worker(args):
     return c["R"], c["E"], dt
 
 
-def cpu_sample(ncores, ring_stride, nlines=100):
+def cpu_sample(cfg, ncores, ring_stride, nlines=None):
     """ncores concurrent single-thread processes, one line each (mirrors the drivers' one process
-    per line chunk: radlite.py:508,593; line_run.pro:173).  Returns (R, E, wall seconds)."""
-    lines = [1 + (k * nlines) // ncores for k in range(ncores)]
+    per line chunk: radlite.py:508,593; line_run.pro:173).  Returns (R, E, slowest process [s], wall [s])."""
+    nl = model_for_bench(cfg, nlines).nlines
+    lines = [1 + (k * nl) // ncores for k in range(ncores)]
     t = time.perf_counter()
     with mp.get_context("spawn").Pool(ncores) as pool:
-        res = pool.map(_cpu_worker, [(il, ring_stride, nlines) for il in lines])
+        res = pool.map(_cpu_worker, [(cfg, il, ring_stride, nlines) for il in lines])
     wall = time.perf_counter() - t
     tmax = max(r[2] for r in res)
     return sum(r[0] for r in res), sum(r[1] for r in res), tmax, wall
 
+
+# seconds one host core needs for one line of the config with every ring traced (measured with the oracle;
+# only used to size the bounded CPU sample)
+CPU_SECONDS_PER_LINE = {1: 5.0, 2: 25.0, 3: 250.0, 4: 25.0, 5: 900.0}
 
 _OUT = sys.stdout
 
@@ -93,31 +132,31 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = args.config
     ncores = os.cpu_count() or 1
     nsteps = args.steps + args.warmup
     # bounded sample: one line per core per step; thin the rings so the whole run stays ~2-3 min
-    per_line_s = 25.0
     budget = 150.0 / max(1, nsteps)
-    stride = max(1, int(np.ceil(per_line_s / budget)))
-    vals, Rs, Es, ts = [], 0.0, 0.0, 0.0
+    stride = max(1, int(np.ceil(CPU_SECONDS_PER_LINE[cfg] / budget)))
+    Rs, Es, ts = 0.0, 0.0, 0.0
     for s in range(nsteps):
-        R, E, tmax, _ = cpu_sample(ncores, stride)
+        R, E, tmax, _ = cpu_sample(cfg, ncores, stride, args.lines)
         if s >= args.warmup:
             Rs += R
             Es += E
             ts += tmax
-            vals.append(R / tmax)
     value = Rs / ts
-    sample = (f"{ncores} of 100 lines per step (one per process), every {stride}th camera ring of "
-              f"each, all channels")
+    nl = model_for_bench(cfg, args.lines).nlines
+    sample = (f"{min(ncores, nl)} of {nl} lines per step (one per process, {ncores} processes), every "
+              f"{stride}th camera ring of each, all channels")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * ts / max(1, args.steps),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": CONFIGS[cfg]["label"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port",
-                         "sample": sample,
+                         "sample": sample, "compiler": _oracle_flags(),
                          "note": "C restatement of the reference path (oracle/); the Fortran binary "
                                  "cannot be built in this image (no Fortran compiler)",
                          "element_integrations_per_s": Es / ts},
@@ -168,95 +207,25 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
 
+    from radlite_b200 import shard
     from radlite_b200.api import Renderer
 
+    cfg = args.config
+    cube = CONFIGS[cfg]["cube"]
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    m = model_for_bench(args.lines)
-    nl, nfr = m.nlines, m.nfr
-    g = Renderer(local)
-    g.load_model(m)
-    arrays = input_arrays(m)
-    h2d = int(sum(a.nbytes for a in arrays))
-    d2h = int(nl * nfr * 8)
-
-    # ---- kernel-only (inputs resident) ----
-    def step_device():
-        g.invalidate_geometry()
-        return g.render_device(1, nl, nfr, m.passband, synth.PARSEC)
-
-    for _ in range(args.warmup):
-        step_device()
-    g.reset_counters()
-    l0 = g.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    t0 = time.perf_counter()
-    ms = np.zeros(5)
-    for _ in range(args.steps):
-        ms += np.array(step_device())
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop() if sampler else None
-    launches = g.launch_count() - l0
-    cnt = g.counters()
-    executed = g.executed_elements()  # element integrations the kernels performed (opaque-wall start skips some)
-    flux_dev = g.fetch_flux(nl, nfr)
-    dev_s = ms[4] * 1e-3  # CUDA-event time of the K steps on the library's stream
-
-    # ---- end to end through the C ABI: host buffers in, host flux out ----
-    def step_e2e():
-        g.load_model(m)
-        return g.render(1, nl, nfr, m.passband, synth.PARSEC)["flux"]
-
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        flux = step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    assert np.array_equal(flux, flux_dev)
-
-    # ---- strong scaling: ONE 100-line spectrum block-partitioned over the ranks ----
-    per = -(-nl // world)  # ceil, like subN = ceil(nlines/ncores) (line_run.pro:79)
-    i0 = min(nl, rank * per)
-    n_loc = max(0, min(per, nl - i0))
-
-    def step_strong():
-        g.invalidate_geometry()
-        if n_loc:
-            g.render_device(i0 + 1, n_loc, nfr, m.passband, synth.PARSEC)
-        if world > 1:  # the only exchange of the path: gather the spectra on rank 0
-            loc = torch.zeros((per, nfr), dtype=torch.float64, device=dev)
-            if n_loc:
-                loc[:n_loc] = torch.from_numpy(g.fetch_flux(n_loc, nfr)).to(dev)
-            parts = [torch.zeros_like(loc) for _ in range(world)] if rank == 0 else None
-            dist.gather(loc, parts, dst=0)
-
-    step_strong()  # (untimed: also opens NCCL's connections for the gather)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_strong()
-    barrier()
-    strong_s = time.perf_counter() - t0
-
-    # ---- reduce over ranks: max time, sum of work ----
     def allmax(x):
         if world == 1:
             return x
@@ -271,12 +240,134 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    dev_s_max, wall_max, e2e_max, strong_max = allmax(dev_s), allmax(wall), allmax(e2e_s), allmax(strong_s)
-    R_tot, E_tot = allsum(cnt["R"]), allsum(cnt["E"])
-    integ_s = allmax(ms[2] * 1e-3)
-    if world > 1:
-        flux_all = [torch.zeros((nl, nfr), dtype=torch.float64, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(torch.from_numpy(flux_dev).to(dev), flux_all, dst=0)
+    m = model_for_bench(cfg, args.lines)
+    nl, nfr = m.nlines, m.nfr
+    g = Renderer(local)
+    g.load_model(m)
+    arrays = input_arrays(m)
+    h2d = int(sum(a.nbytes for a in arrays))
+    nrr, nphi, nray = g.camera_dims()
+    d2h = int(nl * nfr * 8) + (int(nl * (nrr + 1) * nphi * nfr * 8) if cube else 0)
+    K = args.steps
+
+    # ---- one GPU, inputs resident: the whole spectrum (also the reference for the sharded result) ----
+    def step_device():
+        g.invalidate_geometry()
+        return g.render_device(1, nl, nfr, m.passband, synth.PARSEC)
+
+    strong = world > 1
+    sampler = None
+    if not strong:
+        for _ in range(args.warmup):
+            step_device()
+        g.reset_counters()
+        l0 = g.launch_count()
+        sampler = ClockSampler(local)
+        barrier()
+        t0 = time.perf_counter()
+        ms = np.zeros(5)
+        for _ in range(K):
+            ms += np.array(step_device())
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        launches = g.launch_count() - l0
+        cnt = g.counters()
+        executed = g.executed_elements()
+        flux_dev = g.fetch_flux(nl, nfr)
+        step_s = ms[4] * 1e-3 / K  # CUDA-event time per step on the library's stream
+        R_step, E_step, ex_step = cnt["R"] / K, cnt["E"] / K, executed / K
+        integ_ms = ms[2] / K
+        phases = {k: float(v) / K for k, v in
+                  zip(("geometry", "prep_select_scan", "integrate", "fill_flux", "total"), ms)}
+
+        def step_e2e():
+            g.load_model(m)
+            out = g.render(1, nl, nfr, m.passband, synth.PARSEC, want_image=cube)
+            return out["flux"]
+
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            flux = step_e2e()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / K
+        assert np.array_equal(flux, flux_dev)
+        sharded_equal = None
+        blocks = None
+        replicas = None
+    else:
+        # ---- N GPUs: ONE spectrum, camera rings in N blocks of equal estimated work ----
+        ref_flux = g.render(1, nl, nfr, m.passband, synth.PARSEC)["flux"] if rank == 0 else None  # untimed
+        cost = torch.zeros(nrr + 1, dtype=torch.float64, device=dev)
+        if rank == 0:
+            cost = torch.from_numpy(g.plan_costs(1, nl, nfr, m.passband)).to(dev)
+        dist.broadcast(cost, src=0)
+        blocks = shard.split_rings(nrr, world, cost.cpu().numpy())
+        lo, hi = blocks[rank]
+        rs = torch.zeros((nl, nrr + 1, nfr), dtype=torch.float64, device=dev)
+        out = {}
+
+        def step_strong(e2e=False):
+            if e2e:
+                g.load_model(m)
+            else:
+                g.invalidate_geometry()
+            if hi >= lo:
+                t = g.render_rings_device(1, nl, nfr, m.passband, synth.PARSEC, lo, hi, rs.data_ptr())
+            else:
+                rs.zero_()
+                t = [0.0] * 5
+            dist.reduce(rs, dst=0, op=dist.ReduceOp.SUM)  # disjoint rows, the others exactly 0: a concatenation
+            if rank == 0:
+                torch.cuda.current_stream().synchronize()
+                out["flux"] = g.flux_from_rings_device(rs.data_ptr(), nl, nfr, synth.PARSEC)
+            return t
+
+        for _ in range(args.warmup):
+            step_strong()
+        g.reset_counters()
+        l0 = g.launch_count()
+        sampler = ClockSampler(local) if rank == 0 else None
+        barrier()
+        t0 = time.perf_counter()
+        ms = np.zeros(5)
+        for _ in range(K):
+            ms += np.array(step_strong())
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        launches = g.launch_count() - l0
+        cnt = g.counters()
+        executed = g.executed_elements()
+        wall = allmax(wall)
+        step_s = wall / K  # barrier + synchronize on both sides, max over ranks
+        R_step, E_step, ex_step = allsum(cnt["R"]) / K, allsum(cnt["E"]) / K, allsum(executed) / K
+        integ_ms = ms[2] / K
+        phases = {k: float(v) / K for k, v in
+                  zip(("geometry", "prep_select_scan", "integrate", "fill_flux", "total"), ms)}
+        phases_max = {k: allmax(v) for k, v in phases.items()}
+        sharded_equal = bool(np.array_equal(out["flux"], ref_flux)) if rank == 0 else None
+        step_strong(e2e=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_strong(e2e=True)
+        barrier()
+        e2e_s = allmax(time.perf_counter() - t0) / K
+        # N independent spectra (weak scaling of replicas: no exchange at all)
+        step_device()
+        g.reset_counters()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_device()
+        barrier()
+        rep_s = allmax(time.perf_counter() - t0) / K
+        replicas = {"what": f"{world} independent spectra, one per GPU, no exchange (weak scaling)",
+                    "value": allsum(g.counters()["R"]) / K / rep_s, "unit": UNIT, "ms_per_step": 1e3 * rep_s}
+        g.reset_counters()
 
     if rank == 0:
         peak = g.fp64_peak_tflops()
@@ -290,75 +381,80 @@ def run_gpu(args):
         traffic, traffic_src = None, None
         try:
             import glob
-            tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
-            if tfiles and nl == 100:
+            tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r2_cfg{cfg}_*traffic.json")))
+            if tfiles and not strong and not args.lines:
                 tj = json.load(open(tfiles[-1]))
                 traffic, traffic_src = tj["traffic_bytes_per_launch"], os.path.relpath(tfiles[-1], ROOT)
         except (OSError, KeyError, ValueError):
             pass
-        value = R_tot / dev_s_max
-        # dominant kernel: ztile_kernel, one launch per step (100 lines fit one batch)
-        n_launch = args.steps * max(1, -(-nl // max(1, nl)))
-        # the roofline counts the element integrations the kernel EXECUTED; the reference's own count E (it
-        # integrates the segments behind opaque dust too) is reported next to it as *_reference_work
-        E_rank = executed
-        achieved_tf = E_rank * FLOP_PER_ELEMENT / (ms[2] * 1e-3) / 1e12
-        achieved_ref_tf = cnt["E"] * FLOP_PER_ELEMENT / (ms[2] * 1e-3) / 1e12
+        value = R_step / step_s
+        ex_rank = executed / K  # this rank's executed element integrations per step
+        achieved_tf = ex_rank * FLOP_PER_ELEMENT / (integ_ms * 1e-3) / 1e12 if integ_ms > 0 else 0.0
         nodes = g.total_nodes()
-        # algorithmic HBM bytes of one integrate launch: node lists once + per-line cell tables +
-        # image written once (DESIGN.md "Kernels")
-        alg_bytes = nodes * 60.0 + nl * len(m.r) * len(m.theta) * 32.0 + nl * (m.nrr + 1) * m.nphi * nfr * 8.0
+        ncell = len(m.r) * len(m.theta)
+        # algorithmic HBM bytes of the integrate phase: the per-line cell tables and the
+        # line-independent cell fields read once, the spectra (or the cube) written once; the 64-byte node
+        # records are this design's own intermediate (built once per camera, re-read by every line tile)
+        alg_bytes = (4 * nl + 6) * 8.0 * ncell + (nl * (nrr + 1) * nphi * nfr * 8.0 if cube else nl * nfr * 8.0)
+        lb = min(nl, 128)
+        kernel = ("ztile_kernel<9> (one warp = one ray x 16 lines across the lanes x 18 channels) + zcont_kernel "
+                  "(continuum-only ray x line pairs) + center_kernel" if lb >= 8 else
+                  "tile_kernel (block = one ray x <=128 (line, channel) items, staging warp) + center_kernel")
         cpu = None
         if world == 1 and not args.no_cpu:
             ncores = os.cpu_count() or 1
-            R, E, tmax, wall_cpu = cpu_sample(ncores, 1, args.lines)
+            stride = max(1, int(np.ceil(CPU_SECONDS_PER_LINE[cfg] / 30.0)))
+            R, E, tmax, wall_cpu = cpu_sample(cfg, ncores, stride, args.lines)
             cpu = {"value": R / tmax, "unit": UNIT, "cores": ncores, "kind": "port",
-                   "sample": f"{ncores} of {nl} lines (one per process, all rays, all channels), "
-                             f"{tmax:.1f} s",
+                   "sample": f"{min(ncores, nl)} of {nl} lines (one per process, {ncores} processes), every "
+                             f"{stride}th camera ring, all channels, {tmax:.1f} s",
+                   "compiler": _oracle_flags(),
                    "element_integrations_per_s": E / tmax,
                    "note": "C restatement of the reference path (oracle/); Fortran binary not buildable here"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "lines_per_gpu": nl,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": CONFIGS[cfg]["label"], "lines": nl,
                        "l2": "inputs larger than L2: %.2f GB of ray nodes + %.0f MB of per-line cell "
-                             "tables per step, geometry rebuilt every step" % (nodes * 60 / 1e9, nl * len(m.r) * len(m.theta) * 32 / 1e6),
-                       "parallelism": f"lines x rays independent; {world} rank(s), one spectrum each",
-                       "opaque_wall": "library default: ray segments behind tau_dust > 150 (seen from the observer) "
-                                      "are not integrated; image bit-identical to the full walk (DESIGN.md 4.3); "
-                                      "value counts the reference's ray-channel integrations, the roofline the "
-                                      "executed element integrations"},
-            "element_integrations_per_s": E_tot / dev_s_max,
-            "executed_element_fraction": executed / max(1.0, cnt["E"]),
-            "wall_ms_per_step": 1e3 * wall_max / args.steps,
-            "phase_ms_per_step": {k: float(v) / args.steps for k, v in
-                                  zip(("geometry", "prep_select_scan", "integrate", "fill_flux", "total"), ms)},
-            "e2e": {"value": R_tot / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_max / args.steps},
+                             "tables per step, geometry rebuilt every step" % (nodes * 64 / 1e9, nl * ncell * 32 / 1e6),
+                       "parallelism": (f"ONE spectrum over {world} GPUs: camera-ring blocks of equal estimated work x "
+                                       "all lines, ring sums reduced over NCCL to rank 0" if strong else
+                                       "lines x rays independent; 1 GPU"),
+                       "ring_blocks": blocks,
+                       "opaque_wall": "library default (rl_set_wall_tau 64): ray segments whose contribution is provably "
+                                      "below e^-64 of the front-side dust emission are not integrated; R and E are the "
+                                      "reference's counts, the roofline uses the executed element integrations"},
+            "element_integrations_per_s": E_step / step_s,
+            "executed_element_fraction": ex_step / max(1.0, E_step),
+            "wall_ms_per_step": 1e3 * wall / K,
+            "phase_ms_per_step": phases,
+            "e2e": {"value": R_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world if strong else h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
             "gpu_launches": int(launches),
-            "strong": {"what": "wall time of ONE %d-line spectrum block-partitioned over %d GPU(s) incl. "
-                               "final gather" % (nl, world), "ms": 1e3 * strong_max / args.steps},
+            "wall_time_per_spectrum_ms": 1e3 * step_s,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
-                         "traffic_source": traffic_src,
-                         "kernel": "ztile_kernel<9> (formal solution: one warp = one ray x 16 lines across the lanes x 18 channels)",
+                         "traffic_source": traffic_src, "kernel": kernel,
                          "how": "EXECUTED element integrations x 64 FP64 flop (SURVEY.md 8d, exp excluded) / CUDA-event "
-                                "time of the integrate phase (ztile_kernel + centre ray) on the library's stream; "
-                                "peak = DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no "
-                                "FP64 entry); the path is FP64 arithmetic on L2-resident data, so the hbm "
-                                "figure below is reported for completeness only; *_reference_work counts the "
-                                "element integrations the reference performs for the same result (it also "
-                                "integrates the segments behind tau_dust > 150, which ztile_kernel skips)",
-                         "achieved_reference_work": achieved_ref_tf, "frac_reference_work": achieved_ref_tf / peak,
-                         "achieved_exp22": E_rank * (FLOP_PER_ELEMENT + 44.0) / (ms[2] * 1e-3) / 1e12,
-                         "hbm": {"achieved": alg_bytes * args.steps / (ms[2] * 1e-3) / 1e9, "peak": hbm_peak,
-                                 "unit": "GB/s", "frac": alg_bytes * args.steps / (ms[2] * 1e-3) / 1e9 / hbm_peak,
+                                "time of the integrate phase on the library's stream (rank 0); peak = DFMA "
+                                "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); the "
+                                "path is FP64 arithmetic on L2-resident data, the hbm figure is for completeness",
+                         "achieved_exp22": ex_rank * (FLOP_PER_ELEMENT + 44.0) / (integ_ms * 1e-3) / 1e12 if integ_ms > 0 else 0.0,
+                         "hbm": {"algorithmic_bytes": alg_bytes,
+                                 "achieved": alg_bytes / (integ_ms * 1e-3) / 1e9 if integ_ms > 0 else 0.0,
+                                 "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": alg_bytes / (integ_ms * 1e-3) / 1e9 / hbm_peak if integ_ms > 0 else 0.0,
+                                 "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        if strong:
+            line["phase_ms_per_step_max_over_ranks"] = phases_max
+            line["sharded_result_bitwise_equal_to_one_gpu"] = sharded_equal
+            line["replicas"] = replicas
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
@@ -371,7 +467,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lines", type=int, default=100, help="lines per spectrum (BASELINE: 100)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based)")
+    ap.add_argument("--lines", type=int, default=None, help="override the number of lines of the spectrum")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -141,6 +141,26 @@ int rl_flux_from_rings_device(rl_ctx *ctx, int nl, int nfr, double dist_cm, cons
  * (radlite.py:1163-1169). */
 int rl_plan_costs(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double *ring_cost);
 
+/* ---- driver-side ends of the path: no ASCII intermediates for many-line spectra ----------
+ * rl_set_lines_lte replaces rl_set_lines' `popul` by its recipe: LTE populations g exp(-E h c / k T) / Q(T)
+ * (pyradlite radlite.py:1111-1119; PRO/make_levelpop.pro), Q interpolated linearly (extrapolating) in the
+ * tabulated partition sum psum(psum_temp) (radlite.py:1147-1153), values below 1e-99 flushed to 0 -- computed
+ * on the device straight into the table the ray tracer reads (the levelpop_<mol>.dat of BASELINE configs[4] is
+ * 4 GB).  energy_cm[nlevels] in cm^-1, tgas [nr][nth] in K. */
+int rl_set_lines_lte(rl_ctx *ctx, int nlines, int nlevels, const int *lev_up, const int *lev_down,
+                     const double *linefreq, const double *aud, const double *gdeg, const double *energy_cm,
+                     const double *tgas, int npsum, const double *psum_temp, const double *psum);
+/* rl_synthesize_spectrum: pyradlite's RadliteSpectrum._process_spectrum (radlite.py:3001-3184; PRO/genspec.pro),
+ * interpolation 'linear': vel, flux [nl][nfr] as linespectrum_<mol>.dat lists them (velocity ascending, km/s;
+ * F_nu at 1 pc), freq [nl] line centres in Hz, dist_pc, obsres and vsampling in km/s.  Outputs on the
+ * wavelength grid [um] of rl_synthesis_size's nout points: line + continuum, line emission only, continuum
+ * [Jy at dist_pc]. */
+int rl_synthesis_size(int nl, int nfr, const double *vel, const double *freq, double obsres, double vsampling,
+                      int *nout, int *nfull);
+int rl_synthesize_spectrum(rl_ctx *ctx, int nl, int nfr, const double *vel, const double *flux, const double *freq,
+                           double dist_pc, double obsres, double vsampling, double *wavelength, double *spectrum,
+                           double *emission, double *continuum);
+
 /* work counters since the last reset: R = ray-channel integrations (charintline calls the
  * reference would make), E = element integrations (integrate_element_linedust calls incl.
  * sub-grid steps), S = ray segments visited. */

@@ -44,6 +44,13 @@ def load_library() -> C.CDLL:
         _lib.rl_render_rings.restype = C.c_int
         _lib.rl_flux_from_rings.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, dp, dp]
         _lib.rl_flux_from_rings.restype = C.c_int
+        _lib.rl_render_rings_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float)]
+        _lib.rl_render_rings_device.restype = C.c_int
+        _lib.rl_flux_from_rings_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, dp]
+        _lib.rl_flux_from_rings_device.restype = C.c_int
+        _lib.rl_plan_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, dp]
+        _lib.rl_plan_costs.restype = C.c_int
         _lib.rl_launch_count.argtypes = [C.c_void_p]
         _lib.rl_launch_count.restype = C.c_longlong
         _lib.rl_total_nodes.argtypes = [C.c_void_p]
@@ -103,6 +110,30 @@ class Renderer(Binding):
         flux = np.zeros((nl, nfr))
         self._check(self.lib.rl_flux_from_rings(self.ctx, nl, nfr, float(dist_cm), _d(ringsum), _d(flux)))
         return flux
+
+    def render_rings_device(self, iline0, nl, nfr, vmax_kms, dist_cm, ring_lo, ring_hi, d_ringsum: int):
+        """Ring-block render that stays on the device: the ring sums [nl, nrr+1, nfr] are written to the DEVICE
+        address ``d_ringsum`` (e.g. ``tensor.data_ptr()`` of a float64 CUDA tensor), complete on return.
+        Returns the CUDA-event times [ms] like ``render_device``."""
+        ms = (C.c_float * 5)()
+        self._check(self.lib.rl_render_rings_device(self.ctx, int(iline0), int(nl), int(nfr), float(vmax_kms),
+                                                    float(dist_cm), int(ring_lo), int(ring_hi),
+                                                    C.c_void_p(int(d_ringsum)), ms))
+        return [float(x) for x in ms]
+
+    def flux_from_rings_device(self, d_ringsum: int, nl, nfr, dist_cm):
+        """Index-ordered ring sum / distance^2 of the (reduced) ring sums at DEVICE address ``d_ringsum``."""
+        flux = np.zeros((nl, nfr))
+        self._check(self.lib.rl_flux_from_rings_device(self.ctx, int(nl), int(nfr), float(dist_cm),
+                                                       C.c_void_p(int(d_ringsum)), _d(flux)))
+        return flux
+
+    def plan_costs(self, iline0, nl, nfr, vmax_kms):
+        """Work estimate per camera ring (rl_plan_costs): weights for ``shard.split_rings``."""
+        nrr, _, _ = self.camera_dims()
+        cost = np.zeros(nrr + 1)
+        self._check(self.lib.rl_plan_costs(self.ctx, int(iline0), int(nl), int(nfr), float(vmax_kms), _d(cost)))
+        return cost
 
     def set_wall_tau(self, tau: float):
         """Opaque-wall start (include/radlite_b200.h): 0 integrates every segment like the reference."""

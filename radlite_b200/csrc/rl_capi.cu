@@ -320,8 +320,9 @@ int rl_set_medium(rl_ctx *c, const double *rho, const double *abund, const doubl
   return 0;
 }
 
-int rl_set_lines(rl_ctx *c, int nlines, int nlevels, const int *lev_up, const int *lev_down,
-                 const double *linefreq, const double *aud, const double *gdeg, const double *popul) {
+static int set_lines_impl(rl_ctx *c, int nlines, int nlevels, const int *lev_up, const int *lev_down,
+                          const double *linefreq, const double *aud, const double *gdeg, const double *popul,
+                          bool popul_on_device) {
   if (!c->nr) return fail(c, 13, "set_lines: call set_grid first");
   // line.F:1720-1762 checks
   if (nlines < 1) return fail(c, 13, "Minimum of 1 line!");
@@ -347,11 +348,35 @@ int rl_set_lines(rl_ctx *c, int nlines, int nlevels, const int *lev_up, const in
     c->bud[i] = 6.78171833781e46 * aud[i] / (linefreq[i] * linefreq[i] * linefreq[i]);
     c->bdu[i] = c->bud[i] * gratio;
   }
-  CU(c->d_popul.upload(popul, (size_t)c->nr * c->nth * nlevels, c->st));
+  const size_t npop = (size_t)c->nr * c->nth * nlevels;
+  if (popul_on_device) {
+    CU(c->d_popul.ensure(npop));
+    CU(cudaMemcpyAsync(c->d_popul.p, popul, npop * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  } else {
+    CU(c->d_popul.upload(popul, npop, c->st));
+  }
   CU(cudaStreamSynchronize(c->st));
   c->have_line_dust = false;
   return 0;
 }
+
+int rl_set_lines(rl_ctx *c, int nlines, int nlevels, const int *lev_up, const int *lev_down,
+                 const double *linefreq, const double *aud, const double *gdeg, const double *popul) {
+  return set_lines_impl(c, nlines, nlevels, lev_up, lev_down, linefreq, aud, gdeg, popul, false);
+}
+
+// hooks for rl_driver.cu (not part of the ABI)
+int rl_internal_set_lines_device(rl_ctx *c, int nlines, int nlevels, const int *lev_up, const int *lev_down,
+                                 const double *linefreq, const double *aud, const double *gdeg,
+                                 const double *d_popul_src) {
+  return set_lines_impl(c, nlines, nlevels, lev_up, lev_down, linefreq, aud, gdeg, d_popul_src, true);
+}
+int rl_internal_grid_cells(const rl_ctx *c) {
+  cudaSetDevice(c->device);
+  return c->nr * c->nth;
+}
+void rl_internal_count_launches(rl_ctx *c, int n) { c->launches += n; }
+int rl_internal_fail(rl_ctx *c, int code, const char *msg) { return fail(c, code, msg); }
 
 int rl_set_dust(rl_ctx *c, int nspec, const int *nsize, int ncf, const double *cont_freq_nu,
                 const double *kappa_abs, const double *kappa_scat, const double *dust_rho,

@@ -1687,8 +1687,11 @@ struct __align__(16) ZCNode {
   uint32_t fl, icr, needfull, pad;  // segment flags ; crossing type ; line terms needed at this node
 };
 constexpr int kZcWarps = 4;
+#ifndef RL_ZCMINB
+#define RL_ZCMINB 4
+#endif
 
-__global__ void __launch_bounds__(32 * kZcWarps, 6) zcont_kernel(const __grid_constant__ RenderParams P, unsigned tile0,
+__global__ void __launch_bounds__(32 * kZcWarps, RL_ZCMINB) zcont_kernel(const __grid_constant__ RenderParams P, unsigned tile0,
                                                                  unsigned ntile) {
   __shared__ ZCNode s_zc[kZcWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2092,27 +2095,44 @@ __global__ void __launch_bounds__(128) wallcount_kernel(RenderParams P, const in
   int first = max(1, min(nstart[ray], N - 1));             // first segment ztile_kernel / zcont_kernel integrate
   if (tile_shift) first = max(0, min(nstart[ray], N - 1) - 2) + 1;  // tile_kernel starts one segment earlier
   if (first <= 1 || !P.subgrid) return;
+  // the skipped segments that are sub-grid candidates (6 q > 1, flagged by the geometry): usually a handful
+  __shared__ int s_seg[256];
+  __shared__ int s_nseg;
+  if (threadIdx.x == 0) s_nseg = 0;
+  __syncthreads();
+  for (int n = 1 + threadIdx.x; n < first; n += blockDim.x) {
+    const int cx = __ldg(reinterpret_cast<const int *>(P.nodes.rec + n0 + n) + 12);  // cells.x: flags in the top bits
+    if (((uint32_t)cx >> kCellFlagShift) & kFlagSub) {
+      const int k = atomicAdd(&s_nseg, 1);
+      if (k < 256) s_seg[k] = n;
+    }
+  }
+  __syncthreads();
+  const int nseg = s_nseg;
+  if (nseg == 0) return;
   for (int ch = threadIdx.x; ch < P.nfr; ch += blockDim.x) {
     const double vel = __ldg(&P.velz[ch]);
     unsigned cnt = 0;
-    Node p = load_node(P.nodes.rec, n0);
-    for (int n = 1; n < first; n++) {
-      const Node c = load_node(P.nodes.rec, n0 + n);
-      if (c.flags & kFlagSub) {
-        const double ds = c.ds, lwav = 0.5 * (p.lw + c.lw);
-        const double q = fabs((c.dvmu - p.dvmu) / (lwav / 2.99792458e5));
-        const double s_c = ds * (vel - p.dvmu) / (c.dvmu - p.dvmu);
-        const double dls3 = 3.0 * (ds / q);
-        const double sright = s_c + dls3, sleft = s_c - dls3;
-        if (sright > 0.0 && sleft < ds) {
-          const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
-          for (int j = 1; j <= kLgNrMax; j++) {
-            const double sj = sleft + (j - 1) * lg_ds;
-            if (sj > 0.0 && sj < ds) cnt++;
-          }
+    auto count_seg = [&](int n) {
+      const Node p = load_node(P.nodes.rec, n0 + n - 1), c = load_node(P.nodes.rec, n0 + n);
+      const double ds = c.ds, lwav = 0.5 * (p.lw + c.lw);
+      const double q = fabs((c.dvmu - p.dvmu) / (lwav / 2.99792458e5));
+      const double s_c = ds * (vel - p.dvmu) / (c.dvmu - p.dvmu);
+      const double dls3 = 3.0 * (ds / q);
+      const double sright = s_c + dls3, sleft = s_c - dls3;
+      if (sright > 0.0 && sleft < ds) {
+        const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
+        for (int j = 1; j <= kLgNrMax; j++) {
+          const double sj = sleft + (j - 1) * lg_ds;
+          if (sj > 0.0 && sj < ds) cnt++;
         }
       }
-      p = c;
+    };
+    if (nseg <= 256) {
+      for (int k = 0; k < nseg; k++) count_seg(s_seg[k]);
+    } else {  // (list overflow: walk all skipped segments)
+      for (int n = 1; n < first; n++)
+        if (load_node(P.nodes.rec, n0 + n).flags & kFlagSub) count_seg(n);
     }
     s_x[ch] = cnt;
   }
@@ -2147,12 +2167,21 @@ __global__ void __launch_bounds__(128) wallcount_kernel(RenderParams P, const in
 __global__ void __launch_bounds__(256) plan_cost_kernel(RenderParams P, unsigned n_main, unsigned n_all, double *cost) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_all) {
-    const ZTile t = P.ztiles[i];
-    const int N = (int)(P.node_off[t.ray + 1] - P.node_off[t.ray]);
-    const int ns = P.nstart ? max(1, min(P.nstart[t.ray], N - 1)) : 1;
-    const int GW = 32 >> t.lwshift, cw = (t.nchk + GW - 1) / GW, cw3 = 3 * ((cw + 2) / 3);
-    const double per = i < n_main ? 120.0 + 40.0 * cw3 : 100.0;
-    const int ring = t.ray == 0 ? 0 : 1 + (t.ray - 1) / P.nphi;
+    int ray;
+    double per;
+    if (P.use_z) {
+      const ZTile t = P.ztiles[i];
+      const int GW = 32 >> t.lwshift, cw = (t.nchk + GW - 1) / GW, cw3 = 3 * ((cw + 2) / 3);
+      ray = t.ray;
+      per = i < n_main ? 120.0 + 40.0 * cw3 : 100.0;
+    } else {  // tile_kernel: four consumer warps and a staging warp per 128 items
+      const TileDesc t = P.tiles[i];
+      ray = t.ray;
+      per = 100.0 + 3.5 * (double)(t.g1 - t.g0);
+    }
+    const int N = (int)(P.node_off[ray + 1] - P.node_off[ray]);
+    const int ns = P.nstart ? max(1, min(P.nstart[ray], N - 1)) : 1;
+    const int ring = ray == 0 ? 0 : 1 + (ray - 1) / P.nphi;
     atomicAdd(&cost[ring], per * (double)max(0, N - ns));
   }
   if (i < (unsigned)P.nray) {
@@ -2365,23 +2394,13 @@ __global__ void __launch_bounds__(128) ringsum_kernel(RenderParams P, const doub
   } else {
     // skipped channels carry the row's continuum (telescope.F:582-612), never written in this mode
     long long task = ((long long)(1 + (ir - 1) * P.nphi)) * P.nl + l;
-    auto pixel = [&](int ip, long long tk) {
-      const int4 rg = __ldg(&P.rng[tk]);
+    for (int ip = 0; ip < P.nphi; ip++, task += P.nl) {
+      const int4 rg = __ldg(&P.rng[task]);
       const double *row = I - c + (size_t)ip * P.nfr;
-      const bool own = (c == 0) || (c >= rg.x && c <= rg.y) || (c == rg.z) || P.dense[tk];
+      const bool own = (c == 0) || (c >= rg.x && c <= rg.y) || (c == rg.z) || P.dense[task];
       const int src = own ? c : ((rg.w == 0) ? 0 : rg.z);
-      return row[src];
-    };
-    int ip = 0;
-    for (; ip + 4 <= P.nphi; ip += 4, task += 4 * (long long)P.nl) {  // four pixels in flight, summed in index order
-      const double v0 = pixel(ip, task), v1 = pixel(ip + 1, task + P.nl), v2 = pixel(ip + 2, task + 2 * (long long)P.nl),
-                   v3 = pixel(ip + 3, task + 3 * (long long)P.nl);
-      dslum = dslum + v0;
-      dslum = dslum + v1;
-      dslum = dslum + v2;
-      dslum = dslum + v3;
+      dslum = dslum + row[src];
     }
-    for (; ip < P.nphi; ip++, task += P.nl) dslum = dslum + pixel(ip, task);
   }
   dslum = dslum / (1.0 * P.nphi);
   dslum = dslum * surf[ir];

@@ -102,3 +102,39 @@ class OracleEngine:
         for ir in range(ringsum.shape[1]):
             s = s + ringsum[:, ir]
         return s / (dist_cm * dist_cm)
+
+
+def tutorial_model():
+    """The reference's tutorial fixture (tests/golden/tutorial_120x100.npz, built by
+    tests/golden/make_tutorial_fixture.py from DOCS/DOCS_VERSION_1-3/files_for_tutorials/) as a synth.Model: the
+    RADMC grid, dust and star as read, the gas fields and LTE populations as pyradlite derives them
+    (oracle/driver_np.py: gas = 12800 x dust, T_gas = T_dust, constant abundance, Keplerian rotation, alpha-
+    turbulence + thermal width), the 26 12CO lines of 4.6-4.7 um, camera and passband of input_radlite.json."""
+    import os
+
+    from oracle import driver_np as D
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tutorial_120x100.npz"))
+    r, theta = z["r"], z["theta"]
+    nr, nth = len(r), len(theta)
+    tdust = z["dust_temp"][:, :, 0, 0]
+    tgas = D.gas_temperature(tdust)
+    rho = D.gas_density(z["dust_rho"][:, :, 0], float(z["gastodust"]))
+    abund = D.abundance(tdust, float(z["min_abun"]), float(z["max_abun"]))
+    turb = D.turbulence(tdust, float(z["alpha"]), float(z["gamma"]), float(z["mu"]), float(z["molweight"]))
+    vel = np.zeros((nr, nth, 3))
+    vel[..., 2] = D.velocity_phi(r, nth, float(z["mstar"])).T
+    popul = np.ascontiguousarray(np.moveaxis(D.lte_populations(z["ener_cm"], z["gdeg"], tgas, z["psum_temp"], z["psum"]), 0, -1))
+    eerg = 1.986468498e-16 * z["ener_cm"]
+    linefreq = 1.509160e26 * (eerg[z["lev_up"] - 1] - eerg[z["lev_down"] - 1])  # line.F:1903, 1981
+    m = synth.Model(
+        name="tutorial_120x100", r=r, theta=theta, rho=np.ascontiguousarray(rho), abund=abund, vel=vel,
+        linewidth=np.ascontiguousarray(turb / 1.0E5), tgas=tgas, umass_av=float(z["mu"]), molname="12CO",
+        molweight=float(z["molweight"]), ener_cm=z["ener_cm"], gdeg=z["gdeg"], lev_v=z["lev_v"], lev_j=z["lev_j"],
+        lev_up=z["lev_up"], lev_down=z["lev_down"], aud=z["aud"], linefreq=linefreq, popul=popul,
+        nsize=np.array([1], dtype=np.int32), cont_freq_nu=z["cont_freq_nu"], kappa_abs=z["kappa_abs"],
+        kappa_scat=z["kappa_scat"], dust_rho=z["dust_rho"], dust_temp=z["dust_temp"], scati_src=None,
+        rstar=float(z["rstar"]), mstar=float(z["mstar"]), tstar=float(z["tstar"]), starspec_cont=z["starspec_cont"],
+        incl_deg=float(z["incl"]), nphi=int(z["cir_np"]), nrext=int(z["b_extra"]), dbdr=int(z["b_per_r"]),
+        vmax_kms=float(z["passband"]), dv_kms=float(z["vsampling"]), vlsr=float(z["vlsr"]))
+    m.extra = dict(psum_temp=z["psum_temp"], psum=z["psum"])
+    return m
