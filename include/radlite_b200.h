@@ -141,6 +141,20 @@ int rl_flux_from_rings_device(rl_ctx *ctx, int nl, int nfr, double dist_cm, cons
  * (radlite.py:1163-1169). */
 int rl_plan_costs(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double *ring_cost);
 
+/* ---- rectangular imager / position-velocity cube (linespectrum.inp command 2) ---------
+ * rl_set_camera_rect = telescope.F:2229-2475 setup_rays_rectang(nrx,nry,sizepix_x,sizepix_y,anginf,phioffset,
+ * xoffset,yoffset) (call site main.F:800) with imrec_addstar of linespectrum.inp (telescope.F:216): nx, ny even,
+ * pixel sizes and offsets in cm, angles in rad.  rl_render_rect = the rendering part of calc_write_line_posvel
+ * (telescope.F:1828) -> make_freq_image_rectang (:2061): every pixel at every channel (no NONREDUNDANT), rays
+ * that hit the star take its intensity (:4194-4208), pixels off the model take the outer boundary value, and an
+ * unresolved star is smeared over the four central pixels (:2153-2200).
+ *   image, tau [nl][nx][ny][nfr]   imrec_int(inu,ix,iy), imrec_tau(inu,ix,iy) = char_tau (tau may be NULL)
+ * The circular camera (rl_set_camera) and its renders are unaffected. */
+int rl_set_camera_rect(rl_ctx *ctx, double anginf, int nx, int ny, double sizepix_x, double sizepix_y,
+                       double phioffset, double xoffset, double yoffset, double rstar, int addstar);
+int rl_render_rect(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double *image, double *tau,
+                   int *maserflag);
+
 /* ---- driver-side ends of the path: no ASCII intermediates for many-line spectra ----------
  * rl_set_lines_lte replaces rl_set_lines' `popul` by its recipe: LTE populations g exp(-E h c / k T) / Q(T)
  * (pyradlite radlite.py:1111-1119; PRO/make_levelpop.pro), Q interpolated linearly (extrapolating) in the

@@ -53,6 +53,10 @@ struct orc_ctx {
   int have_dust;
   /* camera (common_telescope.h:12-33) */
   int cam_set;
+  /* rectangular camera (telescope.F:2229-2475): rays 1..nrx*nry, then the optional central ray */
+  int rect_set, rays_nrx, rays_nry, imrec_addstar, imrec_starunres;
+  double rays_sizepix_x, rays_sizepix_y;
+  double *rp_b;
   double anginf;
   int nphi, nrext, dbdr, imethod, nrref;
   double rstar;
@@ -1568,6 +1572,151 @@ static void render_line(orc_ctx *c, int iline, int nfr, double passband, double 
   if (!imcir_out) free(imcir_int);
   free(imcir_cont);
   free(velo);
+}
+
+/* ---- telescope.F:2229-2475 setup_rays_rectang ------------------------------------------------------------ */
+static void setup_rays_rectang(orc_ctx *c, int nrx, int nry, double sizepix_x, double sizepix_y, double anginf,
+                               double phioffset, double xoffset, double yoffset) {
+  int ix, iy, ir, nrxhalf, nryhalf;
+  double x_c, y_c, p_c, r_c, theta0, sinth0, xh0, zh0, zh02, dum;
+  size_t maxrays = (size_t)nrx * nry + 3;
+  if ((nrx + 1) / 2 != nrx / 2) STOP(13, "ERROR Telescope: nrx must be even");
+  if ((nry + 1) / 2 != nry / 2) STOP(13, "ERROR Telescope: nry must be even");
+  if (sizepix_x <= 0.0) STOP(13, "setup_rays_rectang(): sizepix_x.le.0");
+  if (sizepix_y <= 0.0) STOP(13, "setup_rays_rectang(): sizepix_y.le.0");
+  if (anginf < 1.e-1) anginf = (double)0.1f; /* telescope.F:2303 assigns the REAL literal 0.1 */
+  theta0 = anginf + 1.e-4;
+  sinth0 = sin(theta0);
+  free(c->rp_x0); free(c->rp_z0); free(c->rp_theta0); free(c->rp_s0); free(c->rp_b);
+  c->rp_x0 = (double *)xcalloc(maxrays, sizeof(double));
+  c->rp_z0 = (double *)xcalloc(maxrays, sizeof(double));
+  c->rp_theta0 = (double *)xcalloc(maxrays, sizeof(double));
+  c->rp_s0 = (double *)xcalloc(maxrays, sizeof(double));
+  c->rp_b = (double *)xcalloc(maxrays, sizeof(double));
+  c->rays_nrx = nrx;
+  c->rays_nry = nry;
+  c->rays_sizepix_x = sizepix_x;
+  c->rays_sizepix_y = sizepix_y;
+  ir = 1;
+  nrxhalf = nrx / 2;
+  nryhalf = nry / 2;
+  for (ix = 1; ix <= nrx; ix++)
+    for (iy = 1; iy <= nry; iy++) {
+      x_c = (ix - nrxhalf - 0.5) * sizepix_x - xoffset;
+      y_c = (iy - nryhalf - 0.5) * sizepix_y - yoffset;
+      r_c = sqrt(x_c * x_c + y_c * y_c);
+      if (x_c == 0.0) x_c = x_c + 0.001 * sizepix_x;
+      p_c = atan(y_c / x_c) - phioffset;
+      if (x_c < 0.0) p_c = p_c + 3.14159265359;
+      while (p_c < 0.0) p_c = p_c + 6.28318530718;
+      while (p_c >= 6.28318530718) p_c = p_c - 6.28318530718;
+      zh0 = -sin(p_c) / sinth0;
+      zh02 = zh0 * zh0;
+      dum = 1.0 - zh02 * sinth0 * sinth0;
+      dum = dum + 1e-4;
+      if (dum < 0.0) STOP(13, "ERROR in setup_rays_rectang");
+      xh0 = (cos(p_c) > 0.0) ? sqrt(dum) : -sqrt(dum);
+      c->rp_x0[ir] = r_c * xh0;
+      c->rp_z0[ir] = r_c * zh0;
+      c->rp_theta0[ir] = theta0;
+      c->rp_s0[ir] = 1.e30;
+      c->rp_b[ir] = r_c;
+      ir = ir + 1;
+    }
+  c->imrec_starunres = 0;
+  if (c->imrec_addstar > 0) {
+    if (xoffset != 0.0 || yoffset != 0.0) STOP(13, "unresolved central star only for star-centred images");
+    c->rp_x0[ir] = 0.0;
+    c->rp_z0[ir] = 0.0;
+    c->rp_theta0[ir] = theta0;
+    c->rp_s0[ir] = 1.e30;
+    ir = ir + 1;
+    if (sizepix_x * sizepix_x + sizepix_y * sizepix_y > c->rstar * c->rstar) c->imrec_starunres = 1;
+  }
+  c->rays_amount = ir - 1;
+  free(c->minvel); free(c->maxvel);
+  c->minvel = (float *)xcalloc((size_t)c->rays_amount + 1, sizeof(float));
+  c->maxvel = (float *)xcalloc((size_t)c->rays_amount + 1, sizeof(float));
+}
+
+int orc_set_camera_rect(orc_ctx *c, double anginf, int nx, int ny, double sizepix_x, double sizepix_y,
+                        double phioffset, double xoffset, double yoffset, double rstar, int addstar) {
+  int code;
+  if (!c->rc) { snprintf(c->err, sizeof c->err, "set_camera_rect: call set_grid first"); return 13; }
+  c->rstar = rstar;
+  c->imrec_addstar = addstar;
+  c->jb_armed = 1;
+  if ((code = setjmp(c->jb)) != 0) { c->jb_armed = 0; return code; }
+  setup_rays_rectang(c, nx, ny, sizepix_x, sizepix_y, anginf, phioffset, xoffset, yoffset);
+  c->jb_armed = 0;
+  c->rect_set = 1;
+  c->cam_set = 0; /* the circular camera's ray arrays were replaced */
+  return 0;
+}
+
+/* ---- telescope.F:2061-2227 make_freq_image_rectang (per line; called from calc_write_line_posvel :1828) ---- */
+#define RECIDX(inu, ix, iy) ((((size_t)((ix)-1)) * (size_t)nry + (size_t)((iy)-1)) * (size_t)nfr + (size_t)((inu)-1))
+int orc_render_rect(orc_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double *image, double *tau,
+                    int *maserflag) {
+  int code, l;
+  if (!c->rc || !c->rho || !c->nlines || !c->have_line_dust || !c->rect_set || !c->bc_set) {
+    snprintf(c->err, sizeof c->err, "stop 13: make_freq_image_rectang(): Ray paramters not yet set");
+    return 13;
+  }
+  if (iline0 < 1 || iline0 + nl - 1 > c->nlines) {
+    snprintf(c->err, sizeof c->err, "render_rect: line range out of bounds");
+    return 13;
+  }
+  for (l = 1; l <= c->nr - 1; l++)
+    if (RC(l + 1) / RC(l) - 1.0 < 1.e4 * TELESC_EPS) {
+      snprintf(c->err, sizeof c->err, "stop 13: radial grid too fine for TELESC_EPS");
+      return 13;
+    }
+  c->jb_armed = 1;
+  if ((code = setjmp(c->jb)) != 0) { c->jb_armed = 0; return code; }
+  for (l = 0; l < nl; l++) {
+    const int iline = iline0 + l, nrx = c->rays_nrx, nry = c->rays_nry;
+    double *im = image + (size_t)l * nrx * nry * nfr, *ta = tau ? tau + (size_t)l * nrx * nry * nfr : 0;
+    const double rmax = RC(c->nr);
+    int ix, iy, inu, iray = 1;
+    c->maserflag = 0;
+    setup_passband_and_bc(c, iline, vmax_kms, nfr);
+    global_prepare_transitions(c);
+    for (ix = 1; ix <= nrx; ix++)
+      for (iy = 1; iy <= nry; iy++) {
+        if (c->rp_b[iray] < 0.999 * rmax) {
+          make_trajectory_c(c, c->rp_x0[iray], c->rp_z0[iray], c->rp_theta0[iray], c->rp_s0[iray]);
+          for (inu = 1; inu <= nfr; inu++) {
+            im[RECIDX(inu, ix, iy)] = charintline(c, iline, inu, iray, 0.0);
+            if (ta) ta[RECIDX(inu, ix, iy)] = c->char_tau;
+          }
+        } else {
+          for (inu = 1; inu <= nfr; inu++) {
+            im[RECIDX(inu, ix, iy)] = (c->out_itype == 3) ? c->isrf_line[inu] : 0.0;
+            if (ta) ta[RECIDX(inu, ix, iy)] = 0.0;
+          }
+        }
+        iray = iray + 1;
+      }
+    if (c->imrec_addstar > 0 && c->imrec_starunres > 0) { /* telescope.F:2153-2200 */
+      const double srat = (3.14159265 * c->rstar * c->rstar) / (4.0 * c->rays_sizepix_x * c->rays_sizepix_y);
+      const double srat1 = 1.0 - srat;
+      make_trajectory_c(c, c->rp_x0[iray], c->rp_z0[iray], c->rp_theta0[iray], c->rp_s0[iray]);
+      for (inu = 1; inu <= nfr; inu++) {
+        double dummy = charintline(c, iline, inu, iray, 0.0);
+        dummy = dummy * srat;
+        ix = nrx / 2;
+        iy = nry / 2;
+        im[RECIDX(inu, ix, iy)] = dummy + srat1 * im[RECIDX(inu, ix, iy)];
+        im[RECIDX(inu, ix + 1, iy)] = dummy + srat1 * im[RECIDX(inu, ix + 1, iy)];
+        im[RECIDX(inu, ix, iy + 1)] = dummy + srat1 * im[RECIDX(inu, ix, iy + 1)];
+        im[RECIDX(inu, ix + 1, iy + 1)] = dummy + srat1 * im[RECIDX(inu, ix + 1, iy + 1)];
+      }
+    }
+    if (maserflag) maserflag[l] = c->maserflag;
+  }
+  c->jb_armed = 0;
+  return 0;
 }
 
 static int check_ready(orc_ctx *c) {

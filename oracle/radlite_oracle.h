@@ -77,6 +77,15 @@ int orc_render(orc_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double 
                double *flux, double *imcir, int *cmask, double *tau_center, int *maserflag,
                double *velo);
 
+/* Rectangular imager / position-velocity cube (linespectrum.inp command 2): telescope.F:2229-2475
+ * setup_rays_rectang(nrx,nry,sizepix_x,sizepix_y,anginf,phioffset,xoffset,yoffset) with imrec_addstar, and
+ * telescope.F:2061-2227 make_freq_image_rectang for each line (driven by calc_write_line_posvel :1828).
+ * image, tau: [nl][nx][ny][nfr] = imrec_int(inu,ix,iy), imrec_tau(inu,ix,iy) (tau may be NULL). */
+int orc_set_camera_rect(orc_ctx *c, double anginf, int nx, int ny, double sizepix_x, double sizepix_y,
+                        double phioffset, double xoffset, double yoffset, double rstar, int addstar);
+int orc_render_rect(orc_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double *image, double *tau,
+                    int *maserflag);
+
 /* work counters accumulated over render calls: R = calls of charintline,
  * E = calls of integrate_element_linedust, S = segments visited (sum over charintline calls) */
 void orc_get_counters(const orc_ctx *c, double *R, double *E, double *S);

@@ -200,6 +200,31 @@ class Binding:
             out["cmask"] = msk
         return out
 
+    # -- rectangular imager / position-velocity cube (linespectrum.inp command 2) ---------------
+    def set_camera_rect(self, anginf, nx, ny, sizepix_x, sizepix_y, phioffset=0.0, xoffset=0.0, yoffset=0.0,
+                        rstar=0.0, addstar=0):
+        f = self._fn("set_camera_rect")
+        f.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int] + [C.c_double] * 6 + [C.c_int]
+        f.restype = C.c_int
+        self._check(f(self.ctx, float(anginf), int(nx), int(ny), float(sizepix_x), float(sizepix_y),
+                      float(phioffset), float(xoffset), float(yoffset), float(rstar), int(addstar)))
+        self._rect = (int(nx), int(ny))
+
+    def render_rect(self, iline0, nl, nfr, vmax_kms, want_tau=True):
+        """Returns dict(image[nl,nx,ny,nfr], tau[nl,nx,ny,nfr]?, maserflag[nl]) = imrec_int / imrec_tau."""
+        f = self._fn("render_rect")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _ip]
+        f.restype = C.c_int
+        nx, ny = self._rect
+        img = np.zeros((nl, nx, ny, nfr))
+        tau = np.zeros((nl, nx, ny, nfr)) if want_tau else None
+        maser = np.zeros(nl, dtype=np.int32)
+        self._check(f(self.ctx, int(iline0), int(nl), int(nfr), float(vmax_kms), _d(img), _d(tau), _i(maser)))
+        out = {"image": img, "maserflag": maser}
+        if want_tau:
+            out["tau"] = tau
+        return out
+
     def load_model(self, m, lines=None):
         """Push a ``synth.Model`` (or any object with the same attributes) through the setters."""
         self.set_grid(m.r, m.theta)

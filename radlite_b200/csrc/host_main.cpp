@@ -20,6 +20,7 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -91,7 +92,7 @@ int main(int argc, char **argv) {
       const char k = argv[i + 1][0];
       const int fw = atoi(argv[i + 2]), fd = atoi(argv[i + 3]);
       const double v = atof(argv[i + 4]);
-      std::string o = k == 'e' ? rlio::fmt_e(v, fw, fd) : k == 'f' ? rlio::fmt_f(v, fw, fd)
+      std::string o = k == 'e' ? rlio::fmt_e(v, fw, fd) : k == 's' ? rlio::fmt_es(v, fw, fd) : k == 'f' ? rlio::fmt_f(v, fw, fd)
                     : k == 'i' ? rlio::fmt_i((long)v, fw) : rlio::fmt_list_real(v);
       printf("[%s]\n", o.c_str());
       return 0;
@@ -155,10 +156,6 @@ int main(int argc, char **argv) {
     }
     return 0;
   }
-  if (w.command == 2) {
-    fprintf(stderr, " linespectrum.inp command 2 (rectangular P/V cube, telescope.F:1828) is not available\n");
-    return 13;
-  }
 
   const auto t0 = std::chrono::steady_clock::now();
   rl_ctx *ctx = nullptr;
@@ -180,6 +177,41 @@ int main(int argc, char **argv) {
   RL(rl_set_bc(ctx, w.in_itype, w.out_itype, ncf, w.cont_freq.data(), w.starspec.data(),
                w.isrf.empty() ? nullptr : w.isrf.data()));
   RL(rl_set_options(ctx, 1, 1, 1.e-3, -1.0));  // configure.h: SUBGRID, NONREDUNDANT, LEVTHRES
+
+  if (w.command == 2) {
+    // linespectrum.inp command 2 -> telesc_command 6: main.F:800 setup_rays_rectang, main.F:1062-1075 the line
+    // loop over calc_write_line_posvel (telescope.F:1828)
+    RL(rl_set_camera_rect(ctx, anginf, w.imr_nx, w.imr_ny, w.imr_spx, w.imr_spy, w.imr_phioff, w.imr_xoff, w.imr_yoff,
+                          w.rstar, w.imrec_addstar));
+    const int nfr = w.nfr;
+    const size_t per = (size_t)w.imr_nx * w.imr_ny * nfr;
+    std::vector<double> image(per), tauim(per), velo(nfr);
+    for (int l = 0; l < w.nlines_render; l++) {
+      const int il = w.ilinestart + l;
+      int maser = 0;
+      printf(" Rendering position-velocity diagram of line %12d\n", il);
+      RL(rl_render_rect(ctx, il, 1, nfr, w.passband, image.data(), tauim.data(), &maser));
+      const double nu0 = std::fabs(w.linefreq[il - 1]), passb = 3.33567e-6 * nu0 * w.passband;
+      for (int k = 0; k < nfr; k++) velo[k] = ((0.0 - passb) + k * (2.0 * passb / (nfr - 1.0))) / w.linefreq[il - 1];
+      try {
+        rlio::write_posvel(rlio::posvel_filename(w.molname, il), w.molname, "./" + w.molfile, w.dist_cm, w.radvelo,
+                           anginf, w.lev_up[il - 1], w.lev_down[il - 1], w.linefreq[il - 1], nfr, w.imr_nx, w.imr_ny,
+                           w.imr_spx, w.imr_spy, w.imr_phioff, w.imr_xoff, w.imr_yoff, velo.data(), image.data(),
+                           tauim.data());
+      } catch (const rlio::Stop &s) {
+        fprintf(stderr, " %s\n", s.msg.c_str());
+        return s.code & 255 ? s.code & 255 : 13;
+      }
+      if (maser) printf(" WARNING: Masing detected!\n Will only warn once for this transition.\n");
+    }
+    rl_destroy(ctx);
+    FILE *fs = fopen("radlite.success", "w");
+    if (fs) {
+      fprintf(fs, " 1\n");
+      fclose(fs);
+    }
+    return 0;
+  }
 
   int nrr = 0, nphi = 0, nray = 0;
   RL(rl_get_camera_dims(ctx, &nrr, &nphi, &nray));

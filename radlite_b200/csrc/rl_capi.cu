@@ -25,6 +25,8 @@ void launch_prep(const PrepParams &P, cudaStream_t st);
 void launch_span(const RenderParams &P, cudaStream_t st);
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st);
 void launch_center(const RenderParams &P, cudaStream_t st);
+void launch_rect(const RenderParams &P, int nx, int ny, double *image, double *tau, double srat, bool star,
+                 cudaStream_t st);
 void launch_zcont(const RenderParams &P, unsigned tile0, unsigned ntile, cudaStream_t st);
 void launch_plan_cost(const RenderParams &P, unsigned n_main, unsigned n_all, double *ring_cost, cudaStream_t st);
 void launch_plan(const RenderParams &P, bool fill, cudaStream_t st);
@@ -128,6 +130,12 @@ struct rl_ctx {
   // geometry
   bool geom_valid = false;
   int geom_ring_lo = 0, geom_ring_hi = 0;  // camera rings the cached node lists cover
+  int geom_kind = 0;                       // camera the cached node lists belong to: 0 circular, 1 rectangular
+  // rectangular camera (telescope.F:2229-2475): ray 0 = the central ray, rays 1..nx*ny the pixels
+  bool rect_set = false;
+  int rect_nx = 0, rect_ny = 0, rect_addstar = 0, rect_starunres = 0;
+  double rect_spx = 0, rect_spy = 0, rect_theta0 = 0, rect_rstar = 0;
+  DevBuf<double> d_rx0, d_rz0, d_rb;
   DevBuf<double> d_tan2;
   long long total_nodes = 0;
   int max_nodes = 0;
@@ -606,33 +614,47 @@ static NodesDev nodes_dev(rl_ctx *c) {
   return n;
 }
 
-static int ensure_geometry(rl_ctx *c, int ring_lo, int ring_hi) {
-  if (c->geom_valid && c->geom_ring_lo == ring_lo && c->geom_ring_hi == ring_hi) return 0;
+static int ensure_geometry(rl_ctx *c, int ring_lo, int ring_hi, int kind = 0) {
+  if (c->geom_valid && c->geom_kind == kind && c->geom_ring_lo == ring_lo && c->geom_ring_hi == ring_hi) return 0;
+  const int nray = kind ? 1 + c->rect_nx * c->rect_ny : c->nray;
   // telescope.F:4323-4340 telescope_check_safety_numbers
   for (int ir = 1; ir <= c->nr - 1; ir++)
     if (c->rc[ir + 2] / c->rc[ir + 1] - 1.0 < 1.e4 * kTelescEps)
       return fail(c, 13, "PROBLEM in telescope: The radial grid resolution is too fine for TELESC_EPS");
   GeomParams P;
   P.g = grid_dev(c);
-  P.nray = c->nray;
-  // ray 0 = the central beam (ring 0), ring ir = rays 1 + (ir-1) nphi .. ir nphi
-  P.ray_lo = ring_lo <= 0 ? 0 : 1 + (ring_lo - 1) * c->nphi;
-  P.ray_hi = ring_hi <= 0 ? 0 : std::min(c->nray - 1, ring_hi * c->nphi);
-  P.x0 = c->d_x0.p;
-  P.z0 = c->d_z0.p;
-  P.theta0 = c->theta0;
-  P.rstar = c->rstar;
+  P.nray = nray;
+  P.rect = kind;
+  P.rb = kind ? c->d_rb.p : nullptr;
+  P.bskip = 0.999 * c->rc[c->nr + 1];
+  if (kind) {
+    P.ray_lo = 0;
+    P.ray_hi = nray - 1;
+    P.x0 = c->d_rx0.p;
+    P.z0 = c->d_rz0.p;
+    P.theta0 = c->rect_theta0;
+    P.rstar = c->rect_rstar;
+    P.rbeam0_center = 0.0;  // rbeam0 = 0 for every ray (telescope.F:2131, 2177)
+  } else {
+    // ray 0 = the central beam (ring 0), ring ir = rays 1 + (ir-1) nphi .. ir nphi
+    P.ray_lo = ring_lo <= 0 ? 0 : 1 + (ring_lo - 1) * c->nphi;
+    P.ray_hi = ring_hi <= 0 ? 0 : std::min(c->nray - 1, ring_hi * c->nphi);
+    P.x0 = c->d_x0.p;
+    P.z0 = c->d_z0.p;
+    P.theta0 = c->theta0;
+    P.rstar = c->rstar;
+    P.rbeam0_center = c->imcir_ri[1];
+  }
   P.in_itype = c->in_itype;
-  P.rbeam0_center = c->imcir_ri[1];
   P.cellS = c->d_cellS.p;
   P.status = c->d_status.p;
   CU(c->d_tan2.ensure((size_t)c->nth + 1));
   launch_tan2(P.g, c->d_tan2.p, c->st);
   P.tan2 = c->d_tan2.p;
-  CU(c->d_node_cnt.ensure((size_t)c->nray + 1));
-  CU(c->d_node_off.ensure((size_t)c->nray + 1));
+  CU(c->d_node_cnt.ensure((size_t)nray + 1));
+  CU(c->d_node_off.ensure((size_t)nray + 1));
   CU(cudaMemsetAsync(c->d_status.p, 0, sizeof(int), c->st));
-  CU(cudaMemsetAsync(c->d_node_cnt.p + c->nray, 0, sizeof(int), c->st));
+  CU(cudaMemsetAsync(c->d_node_cnt.p + nray, 0, sizeof(int), c->st));
   P.node_cnt = c->d_node_cnt.p;
   P.node_off = nullptr;
   P.nodes = NodesDev{};
@@ -644,13 +666,13 @@ static int ensure_geometry(rl_ctx *c, int ring_lo, int ring_hi) {
   {  // node_off = exclusive scan of the counts (64-bit: 3e8 nodes at BASELINE configs[4])
     size_t tmp_bytes = 0;
     auto in = thrust::make_transform_iterator(c->d_node_cnt.p, IntToLL());
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, c->d_node_off.p, c->nray + 1, c->st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, c->d_node_off.p, nray + 1, c->st);
     CU(c->d_scan_tmp.ensure(tmp_bytes));
-    CU(cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, in, c->d_node_off.p, c->nray + 1, c->st));
+    CU(cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, in, c->d_node_off.p, nray + 1, c->st));
     c->launches++;
   }
   long long total = 0;
-  CU(cudaMemcpyAsync(&total, c->d_node_off.p + c->nray, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaMemcpyAsync(&total, c->d_node_off.p + nray, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
   int rcode = check_status(c, "ray geometry, count pass");  // (synchronises the stream)
   if (rcode) return rcode;
   c->total_nodes = total;
@@ -672,12 +694,144 @@ static int ensure_geometry(rl_ctx *c, int ring_lo, int ring_hi) {
   rcode = check_status(c, "ray geometry, fill pass");
   if (rcode) return rcode;
   c->geom_valid = true;
+  c->geom_kind = kind;
   c->geom_ring_lo = ring_lo;
   c->geom_ring_hi = ring_hi;
   return 0;
 }
 
 // ---- render -----------------------------------------------------------------------------------
+// Host tables of the lines il0 .. il0+nb-1 (0-based) of a render batch -- passband (line.F:427-545), star / outer
+// boundary intensity per channel (line.F:3797-3903), Einstein B's, dust bracket (line.F:3560-3574) -- uploaded
+// to the device; velo receives line_dnu / nu0 [nb][nfr].
+static int upload_line_tables(rl_ctx *c, int il0, int nb, int nfr, double vmax_kms, std::vector<double> &velo) {
+  const size_t ncell = (size_t)c->nr * c->nth;
+  // ---- host tables per line: passband, star / outer BC, B's, dust bracket ----
+  std::vector<LineDev> lines(nb);
+  velo.assign((size_t)nb * nfr, 0.0);
+  std::vector<double> line_dnu((size_t)nb * nfr), star((size_t)nb * nfr),
+      isrf((size_t)nb * nfr, 0.0), wgt(nb, 0.0), freq(nb, 0.0);
+  std::vector<int> lup(nb), ldn(nb), inud(nb, 0);
+  for (int l = 0; l < nb; l++) {
+    const int il = il0 + l;
+    const double nu0 = std::fabs(c->linefreq[il]);
+    if (nu0 == 0.0) return fail(c, 13, "Problem in line_setup_passband(): nu0=0 !");
+    // line.F:462-469
+    const double passb = 3.33567e-6 * nu0 * vmax_kms;
+    const double nu1 = 0.0 - passb;
+    const double dnu = 2.0 * passb / (nfr - 1.0);
+    LineDev &L = lines[l];
+    L.nu0 = c->linefreq[il];
+    L.aud = c->aud[il];
+    L.bud = c->bud[il];
+    L.bdu = c->bdu[il];
+    L.dnu0 = nu1;
+    L.ddnu = dnu;
+    L.i_outer = 0.0;
+    L.k_aa = 3.33567e-6 * L.nu0;                    // line.F:2301
+    L.c_src = 5.27296241956e-28 * L.nu0 * L.aud;    // line.F:4571
+    L.c_alp = 5.27296241956e-28 * L.nu0;            // line.F:4584
+    L.inv_nu0 = 1.0 / L.nu0;
+    L.kia = kTabSqrtScale / L.k_aa;  // sqrt(kTabN/ln 2) / k_aa
+    if (c->out_itype == 2) {  // telescope.F:3996-4000
+      const double f = c->linefreq[il];
+      L.i_outer = 1.47455253991e-47 * (f * f * f) / (std::exp(4.7991598e-11 * f / kTempCmb) - 1.0);
+    }
+    const int ncf = (int)c->cfreq_b.size();
+    const double *cf = c->cfreq_b.data();
+    for (int k = 1; k <= nfr; k++) {
+      const double d = nu1 + (k - 1) * dnu;
+      const double fr = nu0 + d;
+      line_dnu[(size_t)l * nfr + k - 1] = d;
+      velo[(size_t)l * nfr + k - 1] = d / c->linefreq[il];
+      const int j = hunt_host(cf, ncf, fr);  // line.F:3835-3846
+      double sv = 0.0;
+      if (!(j == 0 || j == ncf)) {
+        const double w = (fr - cf[j - 1]) / (cf[j] - cf[j - 1]);
+        sv = (1.0 - w) * c->starspec_cont[j - 1] + w * c->starspec_cont[j];
+      }
+      star[(size_t)l * nfr + k - 1] = sv;
+      if (c->out_itype == 3) {  // line.F:3888-3900 (compares with freq_nr = nfr, sic)
+        // the reference's test is j == 0 || j == freq_nr, with freq_nr already confiscated by the passband
+        // (= nfr); it then reads cont_freq_nu(j+1) inside a fixed COMMON array.  Here the bracket must also
+        // lie inside the table (j >= ncf: the line channel is above the last continuum frequency).
+        double iv = 0.0;
+        if (!(j == 0 || j == nfr || j >= ncf)) {
+          const double w = (fr - cf[j - 1]) / (cf[j] - cf[j - 1]);
+          iv = (1.0 - w) * c->isrf_cont[j - 1] + w * c->isrf_cont[j];
+        }
+        isrf[(size_t)l * nfr + k - 1] = iv;
+      }
+    }
+    lup[l] = c->lev_up[il];
+    ldn[l] = c->lev_down[il];
+    if (c->have_dust) {  // line.F:3560-3574
+      const double f = c->linefreq[il];
+      const int j = hunt_host(c->cfreq_d.data(), c->ncf_d, f);
+      inud[l] = j;
+      freq[l] = f;
+      if (!(j == 0 || j == c->ncf_d)) wgt[l] = (f - c->cfreq_d[j - 1]) / (c->cfreq_d[j] - c->cfreq_d[j - 1]);
+    }
+  }
+  CU(c->d_lines.upload(lines, c->st));
+  CU(c->d_line_dnu.upload(line_dnu, c->st));
+  CU(c->d_velo.upload(velo, c->st));
+  // line.F:462-469 without nu0: dnu_k / nu0 is the same velocity grid for every line
+  std::vector<double> velz(nfr);
+  {
+    const double pv = 3.33567e-6 * vmax_kms, dv = 2.0 * pv / (nfr - 1.0);
+    for (int k = 0; k < nfr; k++) velz[k] = (0.0 - pv) + k * dv;
+  }
+  CU(c->d_velz.upload(velz, c->st));
+  CU(c->d_star_line.upload(star, c->st));
+  CU(c->d_isrf_line.upload(isrf, c->st));
+  CU(c->d_lev_up.upload(lup, c->st));
+  CU(c->d_lev_down.upload(ldn, c->st));
+  CU(c->d_inudust.upload(inud, c->st));
+  CU(c->d_wgt.upload(wgt, c->st));
+  CU(c->d_freq.upload(freq, c->st));
+  if (!c->have_dust) {
+    const size_t off = (size_t)il0 * ncell;
+    CU(c->d_ld_src.upload(c->h_ld_src.data() + off, (size_t)nb * ncell, c->st));
+    CU(c->d_ld_alp.upload(c->h_ld_alp.data() + off, (size_t)nb * ncell, c->st));
+  }
+  CU(c->d_cellL.ensure((size_t)nb * ncell));
+  return 0;
+}
+
+// per-line preparation on the device: dust source term and level populations -> cellL (prep_cells_kernel)
+static void run_prep(rl_ctx *c, int nb) {
+  const size_t ncell = (size_t)c->nr * c->nth;
+  PrepParams Q;
+  Q.ncell = (long long)ncell;
+  Q.nl = nb;
+  Q.nlevels = c->nlevels;
+  Q.popul = c->d_popul.p;
+  Q.abund = c->d_abund.p;
+  Q.rho = c->d_rho.p;
+  Q.molpg = 1.0 / (c->umass_av * 1.6726e-24);  // line.F:3998
+  Q.lev_up = c->d_lev_up.p;
+  Q.lev_down = c->d_lev_down.p;
+  Q.use_dust = c->have_dust ? 1 : 0;
+  Q.nspec = c->nspec;
+  Q.maxsize = c->maxsize;
+  Q.ncf = c->ncf_d;
+  Q.nsize = c->d_nsize.p;
+  Q.kabs = c->d_kabs.p;
+  Q.kscat = c->d_kscat.p;
+  Q.drho = c->d_drho.p;
+  Q.dtemp = c->d_dtemp.p;
+  Q.scat = c->have_scat ? c->d_scat.p : nullptr;
+  Q.inudust = c->d_inudust.p;
+  Q.wgt = c->d_wgt.p;
+  Q.freq = c->d_freq.p;
+  Q.ld_src = c->d_ld_src.p;
+  Q.ld_alp = c->d_ld_alp.p;
+  Q.cellL = c->d_cellL.p;
+  launch_prep(Q, c->st);
+  c->launches++;
+}
+
 static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm,
                        double *flux, double *imcir, int *cmask, double *tau_center, int *maserflag,
                        double *velo_out, float *kernel_ms, bool device_only, int ring_lo = 0,
@@ -751,96 +905,10 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
 
   for (int b0 = 0; b0 < nl; b0 += lb) {
     const int nb = std::min(lb, nl - b0);
-    // ---- host tables per line: passband, star / outer BC, B's, dust bracket ----
-    std::vector<LineDev> lines(nb);
-    std::vector<double> line_dnu((size_t)nb * nfr), velo((size_t)nb * nfr), star((size_t)nb * nfr),
-        isrf((size_t)nb * nfr, 0.0), wgt(nb, 0.0), freq(nb, 0.0);
-    std::vector<int> lup(nb), ldn(nb), inud(nb, 0);
-    for (int l = 0; l < nb; l++) {
-      const int il = iline0 - 1 + b0 + l;
-      const double nu0 = std::fabs(c->linefreq[il]);
-      if (nu0 == 0.0) return fail(c, 13, "Problem in line_setup_passband(): nu0=0 !");
-      // line.F:462-469
-      const double passb = 3.33567e-6 * nu0 * vmax_kms;
-      const double nu1 = 0.0 - passb;
-      const double dnu = 2.0 * passb / (nfr - 1.0);
-      LineDev &L = lines[l];
-      L.nu0 = c->linefreq[il];
-      L.aud = c->aud[il];
-      L.bud = c->bud[il];
-      L.bdu = c->bdu[il];
-      L.dnu0 = nu1;
-      L.ddnu = dnu;
-      L.i_outer = 0.0;
-      L.k_aa = 3.33567e-6 * L.nu0;                    // line.F:2301
-      L.c_src = 5.27296241956e-28 * L.nu0 * L.aud;    // line.F:4571
-      L.c_alp = 5.27296241956e-28 * L.nu0;            // line.F:4584
-      L.inv_nu0 = 1.0 / L.nu0;
-      L.kia = kTabSqrtScale / L.k_aa;  // sqrt(kTabN/ln 2) / k_aa
-      if (c->out_itype == 2) {  // telescope.F:3996-4000
-        const double f = c->linefreq[il];
-        L.i_outer = 1.47455253991e-47 * (f * f * f) / (std::exp(4.7991598e-11 * f / kTempCmb) - 1.0);
-      }
-      const int ncf = (int)c->cfreq_b.size();
-      const double *cf = c->cfreq_b.data();
-      for (int k = 1; k <= nfr; k++) {
-        const double d = nu1 + (k - 1) * dnu;
-        const double fr = nu0 + d;
-        line_dnu[(size_t)l * nfr + k - 1] = d;
-        velo[(size_t)l * nfr + k - 1] = d / c->linefreq[il];
-        const int j = hunt_host(cf, ncf, fr);  // line.F:3835-3846
-        double sv = 0.0;
-        if (!(j == 0 || j == ncf)) {
-          const double w = (fr - cf[j - 1]) / (cf[j] - cf[j - 1]);
-          sv = (1.0 - w) * c->starspec_cont[j - 1] + w * c->starspec_cont[j];
-        }
-        star[(size_t)l * nfr + k - 1] = sv;
-        if (c->out_itype == 3) {  // line.F:3888-3900 (compares with freq_nr = nfr, sic)
-          // the reference's test is j == 0 || j == freq_nr, with freq_nr already confiscated by the passband
-          // (= nfr); it then reads cont_freq_nu(j+1) inside a fixed COMMON array.  Here the bracket must also
-          // lie inside the table (j >= ncf: the line channel is above the last continuum frequency).
-          double iv = 0.0;
-          if (!(j == 0 || j == nfr || j >= ncf)) {
-            const double w = (fr - cf[j - 1]) / (cf[j] - cf[j - 1]);
-            iv = (1.0 - w) * c->isrf_cont[j - 1] + w * c->isrf_cont[j];
-          }
-          isrf[(size_t)l * nfr + k - 1] = iv;
-        }
-      }
-      lup[l] = c->lev_up[il];
-      ldn[l] = c->lev_down[il];
-      if (c->have_dust) {  // line.F:3560-3574
-        const double f = c->linefreq[il];
-        const int j = hunt_host(c->cfreq_d.data(), c->ncf_d, f);
-        inud[l] = j;
-        freq[l] = f;
-        if (!(j == 0 || j == c->ncf_d)) wgt[l] = (f - c->cfreq_d[j - 1]) / (c->cfreq_d[j] - c->cfreq_d[j - 1]);
-      }
-    }
-    CU(c->d_lines.upload(lines, c->st));
-    CU(c->d_line_dnu.upload(line_dnu, c->st));
-    CU(c->d_velo.upload(velo, c->st));
-    // line.F:462-469 without nu0: dnu_k / nu0 is the same velocity grid for every line
-    std::vector<double> velz(nfr);
-    {
-      const double pv = 3.33567e-6 * vmax_kms, dv = 2.0 * pv / (nfr - 1.0);
-      for (int k = 0; k < nfr; k++) velz[k] = (0.0 - pv) + k * dv;
-    }
-    CU(c->d_velz.upload(velz, c->st));
-    CU(c->d_star_line.upload(star, c->st));
-    CU(c->d_isrf_line.upload(isrf, c->st));
-    CU(c->d_lev_up.upload(lup, c->st));
-    CU(c->d_lev_down.upload(ldn, c->st));
-    CU(c->d_inudust.upload(inud, c->st));
-    CU(c->d_wgt.upload(wgt, c->st));
-    CU(c->d_freq.upload(freq, c->st));
-    if (!c->have_dust) {
-      const size_t off = (size_t)(iline0 - 1 + b0) * ncell;
-      CU(c->d_ld_src.upload(c->h_ld_src.data() + off, (size_t)nb * ncell, c->st));
-      CU(c->d_ld_alp.upload(c->h_ld_alp.data() + off, (size_t)nb * ncell, c->st));
-    }
+    std::vector<double> velo;
+    rcode = upload_line_tables(c, iline0 - 1 + b0, nb, nfr, vmax_kms, velo);
+    if (rcode) return rcode;
     const size_t ntask = (size_t)nb * c->nray;
-    CU(c->d_cellL.ensure((size_t)nb * ncell));
     CU(c->d_rng.ensure(ntask));
     CU(c->d_masks.ensure(ncell));
     const bool sparse = !imcir && !want_mask;
@@ -869,34 +937,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
 
     // ---- per-line preparation ----
     CU(cudaEventRecord(c->ev[1], c->st));
-    PrepParams Q;
-    Q.ncell = (long long)ncell;
-    Q.nl = nb;
-    Q.nlevels = c->nlevels;
-    Q.popul = c->d_popul.p;
-    Q.abund = c->d_abund.p;
-    Q.rho = c->d_rho.p;
-    Q.molpg = 1.0 / (c->umass_av * 1.6726e-24);  // line.F:3998
-    Q.lev_up = c->d_lev_up.p;
-    Q.lev_down = c->d_lev_down.p;
-    Q.use_dust = c->have_dust ? 1 : 0;
-    Q.nspec = c->nspec;
-    Q.maxsize = c->maxsize;
-    Q.ncf = c->ncf_d;
-    Q.nsize = c->d_nsize.p;
-    Q.kabs = c->d_kabs.p;
-    Q.kscat = c->d_kscat.p;
-    Q.drho = c->d_drho.p;
-    Q.dtemp = c->d_dtemp.p;
-    Q.scat = c->have_scat ? c->d_scat.p : nullptr;
-    Q.inudust = c->d_inudust.p;
-    Q.wgt = c->d_wgt.p;
-    Q.freq = c->d_freq.p;
-    Q.ld_src = c->d_ld_src.p;
-    Q.ld_alp = c->d_ld_alp.p;
-    Q.cellL = c->d_cellL.p;
-    launch_prep(Q, c->st);
-    c->launches++;
+    run_prep(c, nb);
 
     RenderParams P;
     P.g = grid_dev(c);
@@ -1165,6 +1206,143 @@ int rl_plan_costs(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, doubl
   if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
   return render_impl(c, iline0, nl, nfr, vmax_kms, 1.0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                      true, 0, 1 << 30, nullptr, nullptr, ring_cost);
+}
+
+// telescope.F:2229-2475 setup_rays_rectang (+ imrec_addstar of linespectrum.inp, telescope.F:216)
+int rl_set_camera_rect(rl_ctx *c, double anginf, int nx, int ny, double sizepix_x, double sizepix_y, double phioffset,
+                       double xoffset, double yoffset, double rstar, int addstar) {
+  if (!c->nr) return fail(c, 13, "set_camera_rect: call set_grid first");
+  if ((nx + 1) / 2 != nx / 2) return fail(c, 13, "ERROR Telescope: nrx must be even");
+  if ((ny + 1) / 2 != ny / 2) return fail(c, 13, "ERROR Telescope: nry must be even");
+  if (nx < 2 || ny < 2) return fail(c, 13, "ERROR Telescope: image needs at least 2 x 2 pixels");
+  if (sizepix_x <= 0.0) return fail(c, 13, "ERROR: telescope.F/setup_rays_rectang(): sizepix_x.le.0");
+  if (sizepix_y <= 0.0) return fail(c, 13, "ERROR: telescope.F/setup_rays_rectang(): sizepix_y.le.0");
+  if ((long long)nx * ny + 1 > 2000000000LL) return fail(c, 13, "Exceeded maximum number of rays!!");
+  cudaSetDevice(c->device);
+  if (anginf < 1.e-1) anginf = (double)0.1f;  // telescope.F:2303 assigns the REAL literal 0.1
+  const double theta0 = anginf + 1.e-4, sinth0 = std::sin(theta0);
+  const size_t nray = 1 + (size_t)nx * ny;
+  std::vector<double> x0(nray, 0.0), z0(nray, 0.0), rb(nray, 0.0);
+  const int nxh = nx / 2, nyh = ny / 2;
+  size_t ir = 1;
+  for (int ix = 1; ix <= nx; ix++)
+    for (int iy = 1; iy <= ny; iy++) {
+      double x_c = (ix - nxh - 0.5) * sizepix_x - xoffset;
+      const double y_c = (iy - nyh - 0.5) * sizepix_y - yoffset;
+      const double r_c = std::sqrt(x_c * x_c + y_c * y_c);
+      if (x_c == 0.0) x_c = x_c + 0.001 * sizepix_x;
+      double p_c = std::atan(y_c / x_c) - phioffset;
+      if (x_c < 0.0) p_c = p_c + 3.14159265359;
+      while (p_c < 0.0) p_c = p_c + 6.28318530718;
+      while (p_c >= 6.28318530718) p_c = p_c - 6.28318530718;
+      const double zh0 = -std::sin(p_c) / sinth0;
+      const double zh02 = zh0 * zh0;
+      double dum = 1.0 - zh02 * sinth0 * sinth0;
+      dum = dum + 1e-4;
+      if (dum < 0.0) return fail(c, 13, "ERROR in setup_rays_rectang");
+      const double xh0 = (std::cos(p_c) > 0.0) ? std::sqrt(dum) : -std::sqrt(dum);
+      x0[ir] = r_c * xh0;
+      z0[ir] = r_c * zh0;
+      rb[ir] = r_c;
+      ir++;
+    }
+  c->rect_starunres = 0;
+  if (addstar > 0) {
+    if (xoffset != 0.0 || yoffset != 0.0)
+      return fail(c, 13, "PROBLEM: the unresolved central star is only added to star-centred images: put the offsets --> 0");
+    if (sizepix_x * sizepix_x + sizepix_y * sizepix_y > rstar * rstar) c->rect_starunres = 1;
+  }
+  c->rect_nx = nx;
+  c->rect_ny = ny;
+  c->rect_spx = sizepix_x;
+  c->rect_spy = sizepix_y;
+  c->rect_addstar = addstar;
+  c->rect_theta0 = theta0;
+  c->rect_rstar = rstar;
+  CU(c->d_rx0.upload(x0, c->st));
+  CU(c->d_rz0.upload(z0, c->st));
+  CU(c->d_rb.upload(rb, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  c->rect_set = true;
+  if (c->geom_kind == 1) c->geom_valid = false;
+  return 0;
+}
+
+// telescope.F:1828-2057 calc_write_line_posvel (the rendering part) -> :2061 make_freq_image_rectang
+int rl_render_rect(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double *image, double *tau,
+                   int *maserflag) {
+  if (!c->nr || !c->have_medium || !c->nlines || !(c->have_dust || c->have_line_dust) || !c->rect_set || !c->bc_set)
+    return fail(c, 13, "ERROR, make_freq_image_rectang(): Ray paramters not yet set (grid/medium/lines/dust/camera/bc)");
+  if (iline0 < 1 || nl < 1 || iline0 + nl - 1 > c->nlines) return fail(c, 13, "render_rect: line range out of bounds");
+  if (nfr < 2) return fail(c, 13, "Number of frequencies for this line is out of range");
+  if (!image) return fail(c, 13, "render_rect: image pointer is required");
+  if (c->cfreq_b.empty()) return fail(c, 1, "ERROR: Cannot use line stellar BC without having read the stellar spectrum.");
+  if (c->out_itype != 0 && c->out_itype != 2 && c->out_itype != 3)
+    return fail(c, 13, "Telecope: dont know this type of outer BC");
+  if (c->out_itype == 3 && c->isrf_cont.empty())
+    return fail(c, 1, "ERROR: Cannot use line outer BC without having read the interstellar spectrum.");
+  cudaSetDevice(c->device);
+  int rcode = ensure_geometry(c, 0, 0, 1);
+  if (rcode) return rcode;
+  const int nx = c->rect_nx, ny = c->rect_ny;
+  const size_t npix = (size_t)nx * ny, ncell = (size_t)c->nr * c->nth;
+  const int lb = (int)std::max<double>(1.0, std::min<double>(std::min(nl, 64), 1.0e9 / ((double)npix * nfr)));
+  DevBuf<double> d_im, d_ta;
+  CU(d_im.ensure((size_t)lb * npix * nfr));
+  if (tau) CU(d_ta.ensure((size_t)lb * npix * nfr));
+  for (int b0 = 0; b0 < nl; b0 += lb) {
+    const int nb = std::min(lb, nl - b0);
+    std::vector<double> velo;
+    rcode = upload_line_tables(c, iline0 - 1 + b0, nb, nfr, vmax_kms, velo);
+    if (rcode) return rcode;
+    CU(c->d_tau.ensure(nb));
+    CU(c->d_maser.ensure(nb));
+    CU(cudaMemsetAsync(c->d_maser.p, 0, sizeof(int) * nb, c->st));
+    CU(cudaMemsetAsync(c->d_status.p, 0, sizeof(int), c->st));
+    run_prep(c, nb);
+    RenderParams P;
+    memset(&P, 0, sizeof P);
+    P.g = grid_dev(c);
+    P.nray = 1 + (int)npix;
+    P.nphi = 1;
+    P.nrr = 0;
+    P.nl = nb;
+    P.nfr = nfr;
+    P.subgrid = c->subgrid;
+    P.nonredundant = 0;
+    P.levthres = c->levthres;
+    P.starfract = 1.0;  // rbeam0 = 0: a ray that hits the star takes its intensity (telescope.F:4194-4208)
+    P.out_itype = c->out_itype;
+    P.node_off = c->d_node_off.p;
+    P.nodes = nodes_dev(c);
+    P.cellL = c->d_cellL.p;
+    P.ncell = (long long)ncell;
+    P.lines = c->d_lines.p;
+    P.line_dnu = c->d_line_dnu.p;
+    P.velo = c->d_velo.p;
+    P.velz = c->d_velz.p;
+    P.star_line = c->d_star_line.p;
+    P.isrf_line = c->d_isrf_line.p;
+    P.tau_center = c->d_tau.p;
+    P.maser = c->d_maser.p;
+    P.counters = c->d_counters.p;
+    P.status = c->d_status.p;
+    const double srat = (3.14159265 * c->rect_rstar * c->rect_rstar) / (4.0 * c->rect_spx * c->rect_spy);
+    const bool star = c->rect_addstar > 0 && c->rect_starunres > 0;
+    launch_rect(P, nx, ny, d_im.p, tau ? d_ta.p : nullptr, srat, star, c->st);
+    c->launches += star ? 2 : 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(image + (size_t)b0 * npix * nfr, d_im.p, (size_t)nb * npix * nfr * sizeof(double),
+                       cudaMemcpyDeviceToHost, c->st));
+    if (tau)
+      CU(cudaMemcpyAsync(tau + (size_t)b0 * npix * nfr, d_ta.p, (size_t)nb * npix * nfr * sizeof(double),
+                         cudaMemcpyDeviceToHost, c->st));
+    if (maserflag)
+      CU(cudaMemcpyAsync(maserflag + b0, c->d_maser.p, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->st));
+    rcode = check_status(c, "rectangular image");
+    if (rcode) return rcode;
+  }
+  return 0;
 }
 
 int rl_flux_from_rings(rl_ctx *c, int nl, int nfr, double dist_cm, const double *ringsum, double *flux) {

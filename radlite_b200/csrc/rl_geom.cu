@@ -228,7 +228,7 @@ __device__ NodePoint node_point(const GeomParams &P, double x0, double z0, doubl
 // first node); segment bookkeeping of telescope.F:4050-4104, 4129-4193, sub-grid trigger of line.F:4706-4709
 __device__ NodeRec node_record(const GeomParams &P, int iray, const NodePoint &pt, int icr, int ir, double s,
                                bool have_prev, double s_prev, int ir_old, int icr_old, double dvmu_prev,
-                               double lw_prev, int &star_done) {
+                               double lw_prev, int &star_done, bool star_hit) {
   uint32_t flag = (uint32_t)icr;
   double ds = 0.0;
   if (have_prev) {
@@ -244,6 +244,9 @@ __device__ NodeRec node_record(const GeomParams &P, int iray, const NodePoint &p
           flag |= kFlagStar | kFlagInit;
           star_done = 1;
         }
+        // rbeam0 = 0 (rectangular camera): a ray that re-emerges from the central hole with an impact
+        // parameter inside the star has hit it (telescope.F:4194-4208); the render uses star fraction 1
+        if (P.rect && ir == 1 && ir_old == 1 && star_hit) flag |= kFlagStar | kFlagInit;
       } else {
         atomicCAS(P.status, 0, 13);  // inner BC 0 disabled / unknown (telescope.F:4129-4134, 4210)
       }
@@ -292,8 +295,9 @@ __device__ void emit_node(const GeomParams &P, const Ray &R, Emit &E, long long 
     return;
   }
   const NodePoint pt = node_point(P, R.x0, R.z0, R.costh0, znew, bnew, icr, radius, theta, ir, it, s);
+  const bool star_hit = sqrt(R.x0 * R.x0 + R.z0 * R.z0 * (1.0 - R.costh02)) <= P.rstar;  // tr_b (telescope.F:3268)
   P.nodes.rec[idx] = node_record(P, iray, pt, icr, ir, s, E.n > 0, E.s_prev, E.ir_old, E.icr_old, E.dvmu_prev,
-                                 E.lw_prev, E.star_done);
+                                 E.lw_prev, E.star_done, star_hit);
   E.dvmu_prev = pt.dvmu;
   E.lw_prev = pt.lw;
   E.ir_old = ir;
@@ -377,9 +381,10 @@ __global__ void __launch_bounds__(256) node_kernel(GeomParams P, long long ntot)
       lw_prev = pp.lw;
     }
   }
-  int star_done = 1;  // (the star is only ever mixed into the centre ray)
+  int star_done = 1;  // (the circular camera mixes the star into the centre ray only)
+  const bool star_hit = sqrt(x0 * x0 + z0 * z0 * (1.0 - costh0 * costh0)) <= P.rstar;  // tr_b (telescope.F:3268)
   P.nodes.rec[i] = node_record(P, iray, pt, icr, ir, me.s, have_prev, s_prev, ir_old, icr_old, dvmu_prev, lw_prev,
-                               star_done);
+                               star_done, star_hit);
 }
 
 // tan(theta_iy)^2 of the stored hemisphere's cones (telescope.F:2960-2962 evaluates it per ray and cone)
@@ -396,7 +401,8 @@ __global__ void __launch_bounds__(128) geom_kernel(GeomParams P) {
   if (iray >= P.nray) return;
   const GridDev &g = P.g;
   const int nr = g.nr, nt = g.nt;
-  if (iray < P.ray_lo || iray > P.ray_hi) {  // a ray of another rank's ring block
+  if (iray < P.ray_lo || iray > P.ray_hi ||
+      (P.rect && iray > 0 && !(P.rb[iray] < P.bskip))) {  // another rank's ring block / a pixel off the model
     if (COUNT) P.node_cnt[iray] = 0;
     return;
   }

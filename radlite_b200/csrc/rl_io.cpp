@@ -475,6 +475,21 @@ void read_linespectrum_inp(WorkDir &w) {  // telescope.F:86-238
     w.ilinestart = (int)f.integer();
     if (w.command == 1) stop(1, "frequency-integrated images are not available");
     if (w.command != 0 && w.command != 2) stop(13, "linespectrum.inp: unknown command");
+    if (w.command == 2) {  // telescope.F:203-228
+      w.imr_nx = (int)f.integer();
+      w.imr_ny = (int)f.integer();
+      const long isizespecifier = f.integer();
+      double szimx = f.real(), szimy = f.real();
+      szimx = szimx * 0.5;
+      szimy = szimy * 0.5;
+      w.imr_spx = szimx / (w.imr_nx * 0.5);
+      w.imr_spy = szimy / (w.imr_ny * 0.5);
+      w.imr_phioff = f.real();
+      w.imr_xoff = f.real();
+      w.imr_yoff = f.real();
+      w.imrec_addstar = (int)f.integer();
+      if (isizespecifier != 0 && isizespecifier != 1) stop(13, "linespectrum.inp: unknown size specifier");
+    }
   } else {
     stop(13, "linespectrum.inp: unknown object format");
   }
@@ -662,6 +677,19 @@ std::string fmt_e(double v, int w, int d) {
   return pad_left(s, w);
 }
 
+// ESw.d: one non-zero digit before the point; three-digit exponents drop the letter
+std::string fmt_es(double v, int w, int d) {
+  char b[64];
+  snprintf(b, sizeof b, "%.*E", d, v);
+  std::string s = b;
+  const size_t e = s.find('E');
+  if (e != std::string::npos && s.size() - e - 2 > 2) {  // E+123 -> +123 ; C pads the exponent to two digits only
+    s = s.substr(0, e) + s.substr(e + 1);
+  }
+  if ((int)s.size() > w) return std::string(w, '*');
+  return pad_left(s, w);
+}
+
 // list-directed doubleprecision: 17 significant digits; F layout inside 0.1 <= |x| < 1e16 (blank
 // exponent field), otherwise 1PE form with a three-digit exponent; field width 25 + one leading blank
 std::string fmt_list_real(double v) {
@@ -741,6 +769,53 @@ void append_line_spectrum(const std::string &file, int lev_up, int lev_down, dou
 std::string imcir_filename(const std::string &molname, int iline) {
   // telescope.F:1596-1613: only iline < 100 gets a defined name (the reference leaves it unset beyond)
   return "lineposvelcirc_" + molname + "_" + std::to_string(iline) + ".dat";
+}
+
+std::string posvel_filename(const std::string &molname, int iline) {
+  if (iline >= 100) stop(177, "lineposvel file names exist for lines 1..99 only (telescope.F:1967)");
+  return "lineposvel_" + molname + "_" + std::to_string(iline) + ".dat";
+}
+
+void write_posvel(const std::string &file, const std::string &molname, const std::string &molfile, double dist_cm,
+                  double radvelo, double anginf, int lev_up, int lev_down, double linefreq, int nfr, int nx, int ny,
+                  double spx, double spy, double phioff, double xoff, double yoff, const double *velo,
+                  const double *image, const double *tau) {
+  FILE *f = fopen(file.c_str(), "w");
+  if (!f) stop(13, "cannot open " + file);
+  auto a80 = [](const std::string &t) { return (t + std::string(80, ' ')).substr(0, 80); };
+  std::string out;
+  out.reserve((size_t)nfr * nx * ny * 27 + 4096);
+  out += "\n";
+  out += fmt_i(1, 2) + "\n";
+  out += a80(molname) + "\n" + a80(molfile) + "\n";
+  // (57.2957795132 is a REAL literal in the reference, telescope.F:1982)
+  out += fmt_es(dist_cm / 3.08572e18, 12, 4) + fmt_es(radvelo, 12, 4) + fmt_f(anginf * (double)57.2957795132f, 7, 3) + "\n";
+  out += fmt_i(lev_up, 5) + fmt_i(lev_down, 5) + "\n";
+  out += fmt_es(linefreq, 12, 4) + "\n";
+  out += fmt_i(nfr, 5) + "\n";
+  out += fmt_i(nx, 5) + fmt_i(ny, 5) + fmt_es(spx, 12, 4) + fmt_es(spy, 12, 4) + fmt_f(phioff, 7, 3) +
+         fmt_es(xoff, 12, 4) + fmt_es(yoff, 12, 4) + "\n";
+  out += "  \n";
+  for (int k = 0; k < nfr; k++) {  // telescope.F:2002-2007
+    double v = (linefreq + velo[k] * linefreq) - linefreq;
+    v = -2.99792458e5 * v / linefreq;
+    v = v + radvelo;
+    out += fmt_e(v, 10, 3) + " \n";
+  }
+  out += "  \n";
+  const double conv = 3.25465503368e36 / (linefreq * linefreq);
+  for (int k = 0; k < nfr; k++) {  // telescope.F:2017-2027: channel, then iy, then ix
+    for (int iy = 0; iy < ny; iy++)
+      for (int ix = 0; ix < nx; ix++) {
+        const size_t i = ((size_t)ix * ny + iy) * nfr + k;
+        double temp = conv;
+        temp = temp * image[i];
+        out += fmt_es(temp, 12, 5) + " " + fmt_es(tau[i], 12, 5) + " \n";
+      }
+    out += "  \n";
+  }
+  fwrite(out.data(), 1, out.size(), f);
+  fclose(f);
 }
 
 void write_imcir(const std::string &file, int nfr, double nu0, int nphi, int nrr, const double *imcir_ri,

@@ -71,6 +71,9 @@ struct WorkDir {
   std::vector<double> starspec, isrf;  // surface intensity on cont_freq ; ISRF (out_itype 3)
   // linespectrum.inp (telescope.F:86-238) and main.F:202-213
   int style = 0, command = 0, nlines_render = 0, ilinestart = 1;
+  // imager block of command 2 (telescope.F:204-216): pixel counts, pixel sizes [cm], rotation, offsets, star switch
+  int imr_nx = 0, imr_ny = 0, imrec_addstar = 0;
+  double imr_spx = 0.0, imr_spy = 0.0, imr_phioff = 0.0, imr_xoff = 0.0, imr_yoff = 0.0;
   double vmax = 0.0, dv = 0.0, incl_deg = 0.0, radvelo = 0.0;
   std::string molfile, molname;
   int nfr = 0;
@@ -92,6 +95,7 @@ WorkDir read_workdir();
 std::string fmt_e(double v, int w, int d);  // Ew.d
 std::string fmt_f(double v, int w, int d);  // Fw.d
 std::string fmt_i(long v, int w);           // Iw
+std::string fmt_es(double v, int w, int d); // ESw.d
 std::string fmt_list_real(double v);        // write(u,*) of a doubleprecision
 std::string fmt_list_int(long v);           // write(u,*) of an integer
 
@@ -107,6 +111,13 @@ void write_imcir(const std::string &file, int nfr, double nu0, int nphi, int nrr
                  const double *rays_r, const double *velo, const double *image /*[nrr+1][nphi][nfr]*/,
                  const int *cmask);
 std::string imcir_filename(const std::string &molname, int iline);
+// lineposvel_<mol>_<iline>.dat: telescope.F:1934-2040 (calc_write_line_posvel).  image, tau: [nx][ny][nfr];
+// velo[nfr] = line_dnu / nu0
+void write_posvel(const std::string &file, const std::string &molname, const std::string &molfile, double dist_cm,
+                  double radvelo, double anginf, int lev_up, int lev_down, double linefreq, int nfr, int nx, int ny,
+                  double spx, double spy, double phioff, double xoff, double yoff, const double *velo,
+                  const double *image, const double *tau);
+std::string posvel_filename(const std::string &molname, int iline);
 
 // binary dump of the parsed model for the tests: records {name, dtype 'd'|'i', ndim, dims, data}
 void dump_workdir(const WorkDir &w, const std::string &file);

@@ -2226,6 +2226,77 @@ __global__ void __launch_bounds__(128) center_kernel(RenderParams P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Rectangular imager / position-velocity cube (telescope.F:2061-2227 make_freq_image_rectang, driven per line
+// by calc_write_line_posvel :1828): every pixel of an nx x ny Cartesian camera at every channel, no
+// NONREDUNDANT shortcut, with the line-of-sight optical depth char_tau next to the intensity.  The reference
+// marks this mode obsolete (line_params.ini: "image=1 -- do not use"); it is served by the reference-ordered
+// scalar walk (integrate_ray_channel), one thread per (line, pixel, channel).  Ray 0 is the central ray that
+// carries the unresolved star, rays 1 .. nx ny the pixels (ix outer, iy inner: telescope.F:2124-2125).
+// image, tau: [nl][nx][ny][nfr] = imrec_int(inu,ix,iy), imrec_tau(inu,ix,iy).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rect_kernel(RenderParams P, int npix, double *image, double *tau_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)P.nl * npix * P.nfr;
+  const int lane = threadIdx.x & 31;
+  unsigned long long e = 0, sg = 0, r = 0;
+  if (i < n) {
+    const int ch = (int)(i % P.nfr);
+    const int pix = (int)((i / P.nfr) % npix);
+    const int l = (int)(i / ((long long)P.nfr * npix));
+    const int ray = 1 + pix;
+    const long long nn = P.node_off[ray + 1] - P.node_off[ray];
+    double inten, tau = 0.0;
+    if (nn > 0) {
+      unsigned ne;
+      int maser = 0;
+      inten = integrate_ray_channel(P, l, ray, ch, tau, ne, maser);
+      if (maser) atomicOr(&P.maser[l], 1);
+      e = ne;
+      sg = (unsigned long long)(nn - 1);
+      r = 1;
+    } else {  // the pixel misses the model (rp_b >= 0.999 R_nr, telescope.F:2127-2148)
+      inten = (P.out_itype == 3) ? P.isrf_line[(size_t)l * P.nfr + ch] : 0.0;
+    }
+    image[i] = inten;
+    if (tau_out) tau_out[i] = tau;
+  }
+  for (int o = 16; o; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  if (lane == 0 && r) {
+    atomicAdd(&P.counters[0], r);
+    atomicAdd(&P.counters[1], e);
+    atomicAdd(&P.counters[2], sg);
+    atomicAdd(&P.counters[3], e);
+  }
+}
+// the unresolved star smeared over the four central pixels (telescope.F:2153-2200)
+__global__ void __launch_bounds__(128) rect_star_kernel(RenderParams P, int nx, int ny, double srat, double *image) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nl * P.nfr) return;
+  const int l = i / P.nfr, ch = i % P.nfr;
+  double tau;
+  unsigned ne;
+  int maser = 0;
+  double dummy = integrate_ray_channel(P, l, 0, ch, tau, ne, maser);
+  if (maser) atomicOr(&P.maser[l], 1);
+  dummy = dummy * srat;
+  const double srat1 = 1.0 - srat;
+  double *im = image + (size_t)l * nx * ny * P.nfr + ch;
+  for (int dx = 0; dx < 2; dx++)
+    for (int dy = 0; dy < 2; dy++) {
+      double *p = im + ((size_t)(nx / 2 - 1 + dx) * ny + (size_t)(ny / 2 - 1 + dy)) * P.nfr;
+      *p = dummy + srat1 * *p;
+    }
+  atomicAdd(&P.counters[0], 1ull);
+  atomicAdd(&P.counters[1], (unsigned long long)ne);
+  atomicAdd(&P.counters[2], (unsigned long long)(P.node_off[1] - P.node_off[0] - 1));
+  atomicAdd(&P.counters[3], (unsigned long long)ne);
+}
+
 // tiles of a ray: its item list (lines in index order) is cut greedily into runs of at most
 // tile_threads items spanning at most tile_max_lines lines; the item budget is evened out over the
 // ray first.  FILL = false counts the tiles of every ray, FILL = true (after the scan) writes them.
@@ -2498,6 +2569,12 @@ int tile_max_lines(int threads) {
 void launch_plan_cost(const RenderParams &P, unsigned n_main, unsigned n_all, double *ring_cost, cudaStream_t st) {
   const unsigned n = max(n_all, (unsigned)P.nray);
   plan_cost_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, n_main, n_all, ring_cost);
+}
+void launch_rect(const RenderParams &P, int nx, int ny, double *image, double *tau, double srat, bool star,
+                 cudaStream_t st) {
+  const long long n = (long long)P.nl * nx * ny * P.nfr;
+  rect_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, nx * ny, image, tau);
+  if (star) rect_star_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P, nx, ny, srat, image);
 }
 void launch_center(const RenderParams &P, cudaStream_t st) {
   if (P.ring_lo <= 0) center_kernel<<<(P.nl * P.nfr + 127) / 128, 128, 0, st>>>(P);

@@ -83,6 +83,10 @@ struct GeomParams {
   GridDev g;
   int nray;
   int ray_lo, ray_hi;  // rays built by this call (a camera-ring block); the others get no nodes
+  int rect;            // rectangular camera (telescope.F:2229): every ray is traced with rbeam0 = 0 (a ray whose
+                       // impact parameter is inside the star takes the stellar intensity, telescope.F:4194-4208)
+  const double *rb;    // [nray] rectangular camera: pixel radius rp_b; pixels at or beyond bskip are not traced
+  double bskip;        // 0.999 R_nr (telescope.F:2127)
   const double *tan2;  // [nt/2 + 1] tan^2 of the cone angles
   const double *x0;  // [nray]
   const double *z0;

@@ -68,3 +68,33 @@ def test_host_program_fails_like_the_reference(renderer_cls):
     p = wd.run_host(d, check=False)
     assert p.returncode == 91991 % 256 and "91991" in p.stderr
     assert not os.path.exists(os.path.join(d, "radlite.success"))
+
+
+def test_host_program_position_velocity_cube(renderer_cls, oracle_cls):
+    """linespectrum.inp command 2 (main.F:1062-1075 -> calc_write_line_posvel, telescope.F:1828): the host
+    program renders the rectangular cube and writes lineposvel_<mol>_<n>.dat; parsed back it must be the
+    library's image (5 digits: ES12.5) scaled by 3.25465503368d36 / nu0^2, with the optical depth next to it."""
+    m = tiny(2, nlines=2)
+    d = tempfile.mkdtemp(prefix="rlwd_")
+    im = dict(nx=8, ny=6, size_x=100.0 * synth.AU, size_y=90.0 * synth.AU, phioff=0.0, xoff=0.0, yoff=0.0, addstar=1)
+    wd.write_workdir(m, d, image=2, imager=im)
+    p = wd.run_host(d, "--dump", os.path.join(d, "model.bin"))
+    assert p.stdout.count("Rendering position-velocity diagram") == 2
+    assert os.path.exists(os.path.join(d, "radlite.success"))
+    m2 = wd.model_from_dump(m, wd.load_dump(os.path.join(d, "model.bin")))
+    g = renderer_cls(0)
+    g.load_model(m2)
+    g.set_camera_rect(m.anginf, 8, 6, im["size_x"] / 8, im["size_y"] / 6, 0.0, 0.0, 0.0, m2.rstar, 1)
+    gpu = g.render_rect(1, 2, m.nfr, m.passband)
+    o = oracle_cls()
+    o.load_model(m2)
+    o.set_camera_rect(m.anginf, 8, 6, im["size_x"] / 8, im["size_y"] / 6, 0.0, 0.0, 0.0, m2.rstar, 1)
+    ref = o.render_rect(1, 2, m.nfr, m.passband)
+    for k in range(2):
+        c = wd.read_posvel(os.path.join(d, f"lineposvel_moldata_{k + 1}.dat"))
+        assert (c["nx"], c["ny"], c["nfr"]) == (8, 6, m.nfr) and c["lev"] == [int(m.lev_up[k]), int(m.lev_down[k])]
+        conv = 3.25465503368e36 / m2.linefreq[k] ** 2
+        assert np.allclose(c["temp"], conv * gpu["image"][k], rtol=1.0e-5, atol=0.0)
+        assert np.allclose(c["tau"], gpu["tau"][k], rtol=1.0e-5, atol=0.0)
+        assert np.allclose(c["temp"], conv * ref["image"][k], rtol=2.0e-5, atol=0.0)
+        assert abs(c["spx"] - im["size_x"] / 8) < 1e-4 * c["spx"]

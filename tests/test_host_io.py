@@ -21,6 +21,8 @@ pytestmark = pytest.mark.skipif(not os.path.exists(wd.HOST), reason="radlite_b20
     (("f", 7, 3, 15.0), " 15.000"), (("e", 13, 6, 1e-105), " 0.100000-104"), (("e", 12, 6, 1.1306358e12), "0.113064E+13"),
     (("e", 10, 4, 3.21e-9), "0.3210E-08"), (("i", 5, 0, 42), "   42"), (("e", 13, 6, 9.9999996e-5), " 0.100000E-03"),
     (("g", 0, 0, 6.5e13), "    65000000000000.000     "), (("g", 0, 0, -12.5), "   -12.500000000000000     "),
+    (("s", 12, 4, 6.5e13), "  6.5000E+13"), (("s", 12, 5, -1.25e-7), "-1.25000E-07"), (("s", 12, 5, 0.0), " 0.00000E+00"),
+    (("s", 12, 5, 3.3e-105), " 3.30000-105"), (("s", 12, 4, 1.0), "  1.0000E+00"),
 ])
 def test_fortran_edit_descriptors(args, expect):
     import subprocess

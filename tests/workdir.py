@@ -16,7 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "radlite_b200", "radlite_b200_host")
 
 
-def write_workdir(m, d, nlines=None, image=0, comments=True):
+def write_workdir(m, d, nlines=None, image=0, comments=True, imager=None):
+    """``imager`` (with image=2): dict(nx, ny, size_x, size_y [cm, full widths], phioff, xoff, yoff, addstar) -- the
+    block telescope.F:203-216 reads after the line range."""
     os.makedirs(d, exist_ok=True)
     nr, nth = len(m.r), len(m.theta)
     nl = m.nlines if nlines is None else nlines
@@ -117,6 +119,12 @@ def write_workdir(m, d, nlines=None, image=0, comments=True):
     s += "{0:<8.1f}{1:<50s}\n{2:<8.1f}{3:<50s}\n".format(1.0, "Distance in [pc]", m.incl_deg, "Inclination [deg]")
     s += "{0:<8.1f}{1:<60s}\n".format(m.vlsr, "Radial velocity [km/s]")
     s += "{0:<8d}{1:<50s}\n{2:<8d}Starting line to make spectrum/image\n".format(nl, "Nr of lines to make spectrum/image", 1)
+    if image == 2:
+        im = imager
+        s += "{0:<8d}Nr of pixels in x\n{1:<8d}Nr of pixels in y\n{2:<8d}Size specifier (1 = cm)\n".format(im["nx"], im["ny"], 1)
+        s += "{0:<24.16e}Image width in x\n{1:<24.16e}Image width in y\n".format(im["size_x"], im["size_y"])
+        s += "{0:<24.16e}Rotation angle\n{1:<24.16e}X offset\n{2:<24.16e}Y offset\n".format(im["phioff"], im["xoff"], im["yoff"])
+        s += "{0:<8d}Add the unresolved central star\n".format(im["addstar"])
     w("linespectrum.inp", s)
 
 
@@ -204,3 +212,21 @@ def read_imcir(path):
         rows = np.array(take(2 * nphi * nrr)).reshape(nphi, nrr, 2)
         img[k], msk[k] = rows[..., 0], rows[..., 1].astype(int)
     return dict(nfr=nfr, nu0=nu0, nphi=nphi, nrr=nrr, ri=ri, r=r, vel=vel, centre=cen, image=img, cmask=msk)
+
+
+def read_posvel(path):
+    """lineposvel_<mol>_<n>.dat as calc_write_line_posvel writes it (telescope.F:1934-2040)."""
+    L = open(path).read().split("\n")
+    assert L[0].strip() == "" and int(L[1]) == 1
+    dist, vlsr, incl = (float(x) for x in L[4].split())
+    lev = [int(x) for x in L[5].split()]
+    nu0, nfr = float(L[6]), int(L[7])
+    t = L[8].split()
+    nx, ny = int(t[0]), int(t[1])
+    spx, spy, phioff, xoff, yoff = (float(x) for x in t[2:7])
+    tok = " ".join(L[9:]).split()
+    vel = np.array(tok[:nfr], dtype=float)
+    rest = np.array(tok[nfr:nfr + 2 * nfr * nx * ny], dtype=float).reshape(nfr, ny, nx, 2)
+    return dict(dist=dist, vlsr=vlsr, incl=incl, lev=lev, nu0=nu0, nfr=nfr, nx=nx, ny=ny, spx=spx, spy=spy,
+                phioff=phioff, xoff=xoff, yoff=yoff, vel=vel, temp=np.transpose(rest[..., 0], (2, 1, 0)),
+                tau=np.transpose(rest[..., 1], (2, 1, 0)), raw=L)
