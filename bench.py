@@ -325,8 +325,21 @@ def run_gpu(args):
                 out["flux"] = g.flux_from_rings_device(rs.data_ptr(), nl, nfr, synth.PARSEC)
             return t
 
-        for _ in range(args.warmup):
-            step_strong()
+        # warm-up, with the blocks re-cut from the measured device time per rank: the plan's work estimate is a
+        # model; what a rank really needs per unit of estimated work corrects it (two or three rounds settle it)
+        cost_np = cost.cpu().numpy().copy()
+        for w in range(args.warmup):
+            t = step_strong()
+            tk = torch.tensor([t[4]], dtype=torch.float64, device=dev)
+            allt = [torch.zeros_like(tk) for _ in range(world)]
+            dist.all_gather(allt, tk)
+            allt = np.array([float(x.item()) for x in allt])
+            if w < args.warmup - 1 and allt.min() > 0:
+                for k, (a, b) in enumerate(blocks):
+                    if b >= a:
+                        cost_np[a:b + 1] *= allt[k] / max(cost_np[a:b + 1].sum(), 1e-300)
+                blocks = shard.split_rings(nrr, world, cost_np)
+                lo, hi = blocks[rank]
         g.reset_counters()
         l0 = g.launch_count()
         sampler = ClockSampler(local) if rank == 0 else None

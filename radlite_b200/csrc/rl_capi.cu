@@ -21,6 +21,8 @@
 namespace rl {
 void launch_geom(const GeomParams &P, bool count, cudaStream_t st);
 void launch_tan2(const GridDev &g, double *tan2, cudaStream_t st);
+void launch_roots(const GeomParams &P, cudaStream_t st);
+size_t geom_smem_bytes(const GridDev &g);
 void launch_prep(const PrepParams &P, cudaStream_t st);
 void launch_span(const RenderParams &P, cudaStream_t st);
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st);
@@ -137,6 +139,8 @@ struct rl_ctx {
   double rect_spx = 0, rect_spy = 0, rect_theta0 = 0, rect_rstar = 0;
   DevBuf<double> d_rx0, d_rz0, d_rb;
   DevBuf<double> d_tan2;
+  DevBuf<double4> d_thr;  // cone roots of the rays being built (roots_kernel)
+  DevBuf<double2> d_rrt;  // sphere roots
   long long total_nodes = 0;
   int max_nodes = 0;
   DevBuf<int> d_node_cnt;
@@ -648,13 +652,29 @@ static int ensure_geometry(rl_ctx *c, int ring_lo, int ring_hi, int kind = 0) {
   P.in_itype = c->in_itype;
   P.cellS = c->d_cellS.p;
   P.status = c->d_status.p;
+  if (geom_smem_bytes(P.g) > 200 * 1024)
+    return fail(c, 13, "grid has too many points per axis for the geometry kernel's shared-memory stage");
   CU(c->d_tan2.ensure((size_t)c->nth + 1));
   launch_tan2(P.g, c->d_tan2.p, c->st);
   P.tan2 = c->d_tan2.p;
+  {
+    // (the root tables serve the warp-per-ray kernels: launch_geom picks them below 16000 rays)
+    const size_t nblock = (size_t)(P.ray_hi - P.ray_lo + 1);
+    P.thr = nullptr;
+    P.rrt = nullptr;
+    if (nblock < (size_t)kGeomWarpMax) {
+      CU(c->d_thr.ensure(nblock * (size_t)c->nth));
+      CU(c->d_rrt.ensure(nblock * (size_t)(c->nr + 1)));
+      P.thr = c->d_thr.p;
+      P.rrt = c->d_rrt.p;
+      launch_roots(P, c->st);
+      c->launches++;
+    }
+  }
   CU(c->d_node_cnt.ensure((size_t)nray + 1));
   CU(c->d_node_off.ensure((size_t)nray + 1));
   CU(cudaMemsetAsync(c->d_status.p, 0, sizeof(int), c->st));
-  CU(cudaMemsetAsync(c->d_node_cnt.p + nray, 0, sizeof(int), c->st));
+  CU(cudaMemsetAsync(c->d_node_cnt.p, 0, sizeof(int) * ((size_t)nray + 1), c->st));  // rays outside the block: no nodes
   P.node_cnt = c->d_node_cnt.p;
   P.node_off = nullptr;
   P.nodes = NodesDev{};
@@ -682,6 +702,7 @@ static int ensure_geometry(rl_ctx *c, int ring_lo, int ring_hi, int kind = 0) {
   const size_t n = (size_t)c->total_nodes;
   if ((size_t)c->nr * c->nth > (size_t)kCellMask) return fail(c, 13, "grid has too many cells for the node record");
   if (c->nr >= 32768 || c->nt >= 32768) return fail(c, 13, "grid has too many points per axis for the node scratch");
+
   CU(c->d_nrec.ensure(n));
   CU(c->d_light.ensure(std::max<size_t>(1, n)));
   P.node_off = c->d_node_off.p;

@@ -15,6 +15,10 @@ constexpr int kMaxExtra = 40;  // 2 + 4*RAYADPT*2 = 34 used
 constexpr int kLgNrMax = 31;   // line.F:4657-4661
 constexpr int kTileIpt = 1;        // ray-channel items per tile_kernel thread
 constexpr int kTileChunk = 31;     // nodes staged per chunk (upper bound: chunk + 1 previous node = one per producer lane)
+#ifndef RL_GEOM_WARP_MAX
+#define RL_GEOM_WARP_MAX (1 << 30)
+#endif
+constexpr int kGeomWarpMax = RL_GEOM_WARP_MAX;  // rays of a build below which geom_kernel runs one warp per ray
 constexpr int kSpanThreads = 128;  // span_kernel block = lines per batch upper bound (one mask bit per line)
 
 // exp table of the integrate kernel: 2^(j / kTabN), j = 0..kTabN-1.  16 entries of 8 bytes span the 32
@@ -88,6 +92,8 @@ struct GeomParams {
   const double *rb;    // [nray] rectangular camera: pixel radius rp_b; pixels at or beyond bskip are not traced
   double bskip;        // 0.999 R_nr (telescope.F:2127)
   const double *tan2;  // [nt/2 + 1] tan^2 of the cone angles
+  double4 *thr;        // [rays of the block][nt/2] cone roots and their radii (roots_kernel)
+  double2 *rrt;        // [rays of the block][nr+1] sphere roots (roots_kernel)
   const double *x0;  // [nray]
   const double *z0;
   double theta0;
