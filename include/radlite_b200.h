@@ -123,6 +123,12 @@ int rl_render_rings(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, d
                     int ring_lo, int ring_hi, double *ringsum, double *imcir);
 int rl_flux_from_rings(rl_ctx *ctx, int nl, int nfr, double dist_cm, const double *ringsum,
                        double *flux);
+/* the same with everything a cube run writes (SAVE_IMCIR, telescope.F:1346-1371): the rows of the block in imcir
+ * and cmask (same shapes as in rl_render; rows outside the block are left untouched), tau_center and maserflag
+ * (tau_center is only set by the block that holds ring 0; maserflag is the block's own: OR them) */
+int rl_render_rings_cube(rl_ctx *ctx, int iline0, int nl, int nfr, double vmax_kms, double dist_cm, int ring_lo,
+                         int ring_hi, double *ringsum, double *imcir, int *cmask, double *tau_center,
+                         int *maserflag);
 
 /* Device-resident variants for sharded renders (one process per GPU): rl_render_rings_device leaves nothing
  * on the host and copies the ring sums [nl][nrr+1][nfr] into d_ringsum, a DEVICE pointer of the caller (the

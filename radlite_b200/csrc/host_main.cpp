@@ -65,6 +65,112 @@ static const Rec *find_rec(const std::vector<std::pair<std::string, Rec>> &v, co
   return nullptr;
 }
 
+static void append_record(FILE *f, const std::string &name, char dt, const std::vector<long long> &dims,
+                          const void *data) {
+  char nm[32] = {0};
+  snprintf(nm, sizeof nm, "%s", name.c_str());
+  const int nd = (int)dims.size();
+  size_t n = 1;
+  for (long long d : dims) n *= (size_t)d;
+  fwrite(nm, 1, 32, f);
+  fwrite(&dt, 1, 1, f);
+  fwrite(&nd, sizeof nd, 1, f);
+  fwrite(dims.data(), sizeof(long long), dims.size(), f);
+  fwrite(data, dt == 'd' ? sizeof(double) : sizeof(int), n, f);
+}
+
+// --assemble: the part files of a ring-sharded run (one process per GPU, --rings lo:hi --part FILE) -> the
+// output files of the unsharded run, byte for byte: the ring sums of disjoint blocks add exactly, the flux is
+// the reference's index-ordered sum (telescope.F:1388-1433), cube and mask rows are placed where they belong.
+static int assemble(const rlio::WorkDir &w, const std::vector<std::string> &parts, bool imcir) {
+  const int nl = w.nlines_render, nfr = w.nfr;
+  int nrr = -1, nphi = 0;
+  std::vector<std::vector<std::pair<std::string, Rec>>> recs(parts.size());
+  std::vector<int> covered;
+  for (size_t k = 0; k < parts.size(); k++) {
+    if (!load_records(parts[k], recs[k])) {
+      fprintf(stderr, " cannot read part file %s\n", parts[k].c_str());
+      return 13;
+    }
+    const Rec *h = find_rec(recs[k], "part");
+    if (!h || h->i.size() < 7 || h->i[2] != nl || h->i[3] != nfr || (imcir && !h->i[6])) {
+      fprintf(stderr, " part file %s does not belong to this run\n", parts[k].c_str());
+      return 13;
+    }
+    if (nrr < 0) {
+      nrr = h->i[4];
+      nphi = h->i[5];
+      covered.assign(nrr + 1, 0);
+    }
+    for (int ir = h->i[0]; ir <= h->i[1]; ir++) covered[ir]++;
+  }
+  for (int ir = 0; ir <= nrr; ir++)
+    if (covered[ir] != 1) {
+      fprintf(stderr, " ring %d is covered %d times by the part files\n", ir, covered[ir]);
+      return 13;
+    }
+  const Rec *rr = find_rec(recs[0], "rays_r"), *ri = find_rec(recs[0], "imcir_ri");
+  const std::string specfile = "linespectrum_" + w.molname + ".dat";
+  const double anginf = w.incl_deg * 0.0174532925199;
+  try {
+    rlio::write_spectrum_header(specfile, w.molname, "./" + w.molfile, nl, nfr, w.dist_cm, w.radvelo, anginf, w.style);
+    const size_t per = (size_t)(nrr + 1) * nphi * nfr;
+    std::vector<double> ring((size_t)(nrr + 1) * nfr), flux(nfr), velo(nfr), cube;
+    std::vector<int> mask;
+    if (imcir) {
+      cube.resize(per);
+      mask.resize(per);
+    }
+    for (int l = 0; l < nl; l++) {
+      const int il = w.ilinestart + l;
+      std::fill(ring.begin(), ring.end(), 0.0);
+      int maser = 0;
+      for (size_t k = 0; k < parts.size(); k++) {
+        const Rec *h = find_rec(recs[k], "part");
+        const int lo = h->i[0], hi = h->i[1];
+        const Rec *rs = find_rec(recs[k], ("ringsum_" + std::to_string(l)).c_str());
+        const Rec *ms = find_rec(recs[k], ("maser_" + std::to_string(l)).c_str());
+        if (!rs) return 13;
+        for (size_t i = 0; i < ring.size(); i++) ring[i] = ring[i] + rs->d[i];  // x + 0 outside the block
+        if (ms && ms->i[0]) maser = 1;
+        if (imcir) {
+          const Rec *cb = find_rec(recs[k], ("cube_" + std::to_string(l)).c_str());
+          const Rec *mk = find_rec(recs[k], ("mask_" + std::to_string(l)).c_str());
+          if (!cb || !mk) return 13;
+          const size_t o = (size_t)lo * nphi * nfr, n = (size_t)(hi - lo + 1) * nphi * nfr;
+          std::copy(cb->d.begin(), cb->d.begin() + n, cube.begin() + o);
+          std::copy(mk->i.begin(), mk->i.begin() + n, mask.begin() + o);
+        }
+      }
+      const double dist2 = w.dist_cm * w.dist_cm;
+      for (int c = 0; c < nfr; c++) {  // telescope.F:1388-1433: centre, then rings 1..nrr, in index order
+        double slum = 0.0;
+        for (int ir = 0; ir <= nrr; ir++) slum = slum + ring[(size_t)ir * nfr + c];
+        flux[c] = slum / dist2;
+      }
+      const double nu0 = std::fabs(w.linefreq[il - 1]), passb = 3.33567e-6 * nu0 * w.passband;
+      const double nu1 = 0.0 - passb, dnu = 2.0 * passb / (nfr - 1.0);
+      for (int k = 1; k <= nfr; k++) velo[k - 1] = (nu1 + (k - 1) * dnu) / w.linefreq[il - 1];
+      if (imcir)
+        rlio::write_imcir(rlio::imcir_filename(w.molname, il), nfr, w.linefreq[il - 1], nphi, nrr, ri->d.data(),
+                          rr->d.data(), velo.data(), cube.data(), mask.data());
+      rlio::append_line_spectrum(specfile, w.lev_up[il - 1], w.lev_down[il - 1], w.linefreq[il - 1], nfr, velo.data(),
+                                 flux.data(), w.radvelo);
+      if (maser) printf(" WARNING: Masing detected! (line %d)\n", il);
+      printf(" Rendered spectrum of line %12d\n", il);
+    }
+  } catch (const rlio::Stop &s) {
+    fprintf(stderr, " %s\n", s.msg.c_str());
+    return 13;
+  }
+  FILE *f = fopen("radlite.success", "w");
+  if (f) {
+    fprintf(f, " 1\n");
+    fclose(f);
+  }
+  return 0;
+}
+
 static int fail_rl(rl_ctx *ctx, int code) {
   fprintf(stderr, " radlite_b200: %s\n", rl_last_error(ctx));
   return code > 0 ? (code & 255 ? code & 255 : 1) : 1;
@@ -77,7 +183,9 @@ static int fail_rl(rl_ctx *ctx, int code) {
   } while (0)
 
 int main(int argc, char **argv) {
-  std::string dir, dump, replay;
+  std::string dir, dump, replay, part;
+  std::vector<std::string> assemble_parts;
+  int ring_lo = -1, ring_hi = -1;
   int device = 0;
   bool imcir = std::strstr(argv[0], "imcir") != nullptr, parse_only = false;
   if (const char *e = getenv("RADLITE_B200_DEVICE")) device = atoi(e);
@@ -96,6 +204,13 @@ int main(int argc, char **argv) {
                     : k == 'i' ? rlio::fmt_i((long)v, fw) : rlio::fmt_list_real(v);
       printf("[%s]\n", o.c_str());
       return 0;
+    }
+    else if (a == "--rings" && i + 1 < argc) {  // camera-ring block lo:hi of a sharded run (0 = central beam)
+      if (sscanf(argv[++i], "%d:%d", &ring_lo, &ring_hi) != 2) return 2;
+    }
+    else if (a == "--part" && i + 1 < argc) part = argv[++i];
+    else if (a == "--assemble") {
+      while (i + 1 < argc && argv[i + 1][0] != '-') assemble_parts.push_back(argv[++i]);
     }
     else if (a == "--imcir") imcir = true;
     else if (a == "--parse-only") parse_only = true;
@@ -127,6 +242,7 @@ int main(int argc, char **argv) {
          w.molname.c_str(), w.nlevels, w.nlines, w.ilinestart, w.ilinestart + w.nlines_render - 1, w.nfr,
          w.passband);
   if (parse_only) return 0;
+  if (!assemble_parts.empty()) return assemble(w, assemble_parts, imcir);
   if (!replay.empty()) {  // format test: write the outputs from stored results, no GPU involved
     std::vector<std::pair<std::string, Rec>> recs;
     if (!load_records(replay, recs)) return 13;
@@ -216,6 +332,44 @@ int main(int argc, char **argv) {
   int nrr = 0, nphi = 0, nray = 0;
   RL(rl_get_camera_dims(ctx, &nrr, &nphi, &nray));
   const int nl = w.nlines_render, nfr = w.nfr;
+  if (ring_lo >= 0) {
+    // one rank of a ring-sharded run: render the block, leave its ring sums (and cube / mask rows) in a part
+    // file; `--assemble` of all part files writes the output files of the unsharded run
+    if (part.empty() || ring_hi < ring_lo || ring_hi > nrr) {
+      fprintf(stderr, " --rings lo:hi needs --part FILE and 0 <= lo <= hi <= %d\n", nrr);
+      return 2;
+    }
+    FILE *pf = fopen(part.c_str(), "wb");
+    if (!pf) return 13;
+    std::vector<double> rays_r(nrr + 1), ri(nrr + 2);
+    RL(rl_get_rings(ctx, rays_r.data(), ri.data()));
+    const int hdr[7] = {ring_lo, ring_hi, nl, nfr, nrr, nphi, imcir ? 1 : 0};
+    append_record(pf, "part", 'i', {7}, hdr);
+    append_record(pf, "rays_r", 'd', {nrr + 1}, rays_r.data());
+    append_record(pf, "imcir_ri", 'd', {nrr + 2}, ri.data());
+    const size_t per = (size_t)(nrr + 1) * nphi * nfr, slab = (size_t)(ring_hi - ring_lo + 1) * nphi * nfr;
+    std::vector<double> ring((size_t)(nrr + 1) * nfr), cube;
+    std::vector<int> mask;
+    if (imcir) {
+      cube.resize(per);
+      mask.resize(per);
+    }
+    for (int l = 0; l < nl; l++) {
+      double tau = 0.0;
+      int maser = 0;
+      RL(rl_render_rings_cube(ctx, w.ilinestart + l, 1, nfr, w.passband, w.dist_cm, ring_lo, ring_hi, ring.data(),
+                              imcir ? cube.data() : nullptr, imcir ? mask.data() : nullptr, &tau, &maser));
+      append_record(pf, "ringsum_" + std::to_string(l), 'd', {nrr + 1, nfr}, ring.data());
+      append_record(pf, "maser_" + std::to_string(l), 'i', {1}, &maser);
+      if (imcir) {
+        append_record(pf, "cube_" + std::to_string(l), 'd', {(long long)slab}, cube.data() + (size_t)ring_lo * nphi * nfr);
+        append_record(pf, "mask_" + std::to_string(l), 'i', {(long long)slab}, mask.data() + (size_t)ring_lo * nphi * nfr);
+      }
+    }
+    fclose(pf);
+    rl_destroy(ctx);
+    return 0;
+  }
   const std::string specfile = "linespectrum_" + w.molname + ".dat";
   // main.F:1037 header_line_spectrum
   try {

@@ -870,7 +870,6 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
   ring_hi = std::min(ring_hi, c->nrr);
   if (ring_lo < 0 || ring_lo > ring_hi) return fail(c, 13, "render: ring block out of bounds");
   const bool ring_block = ring_lo > 0 || ring_hi < c->nrr;
-  if (ring_block && cmask) return fail(c, 13, "render: cmask is not available for a ring block");
   if (c->bc_set && c->cfreq_b.empty())
     return fail(c, 1, "ERROR: Cannot use line stellar BC without having read the stellar spectrum.");
   if (c->out_itype == 1) return fail(c, 13, "Outer BC type 1 not allowed for telescope");
@@ -1143,9 +1142,16 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
       if (ringsum)
         CU(cudaMemcpyAsync(ringsum + (size_t)b0 * (c->nrr + 1) * nfr, c->d_ring.p,
                            (size_t)nb * (c->nrr + 1) * nfr * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-      if (want_mask)
+      if (want_mask && !ring_block)
         CU(cudaMemcpyAsync(cmask + (size_t)b0 * nrow * nfr, c->d_cmask_out.p,
                            (size_t)nb * nrow * nfr * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+      if (want_mask && ring_block)  // the mask rows of this block (telescope.F:548,575 set them per pixel)
+        for (int l = 0; l < nb; l++) {
+          const size_t o = ((size_t)l * nrow + (size_t)ring_lo * c->nphi) * nfr;
+          CU(cudaMemcpyAsync(cmask + (size_t)b0 * nrow * nfr + o, c->d_cmask_out.p + o,
+                             (size_t)(ring_hi - ring_lo + 1) * c->nphi * nfr * sizeof(int), cudaMemcpyDeviceToHost,
+                             c->st));
+        }
       if (tau_center)
         CU(cudaMemcpyAsync(tau_center + b0, c->d_tau.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->st));
       if (maserflag)
@@ -1199,6 +1205,15 @@ int rl_render_rings(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, dou
   std::vector<double> flux((size_t)std::max(nl, 1) * std::max(nfr, 1));
   return render_impl(c, iline0, nl, nfr, vmax_kms, dist_cm, flux.data(), imcir, nullptr, nullptr, nullptr,
                      nullptr, nullptr, false, ring_lo, ring_hi, ringsum);
+}
+
+int rl_render_rings_cube(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm, int ring_lo,
+                         int ring_hi, double *ringsum, double *imcir, int *cmask, double *tau_center, int *maserflag) {
+  if (!ringsum) return fail(c, 13, "render_rings_cube: ringsum pointer is required");
+  if (!c->cam_set) return fail(c, 13, "Ray paramters not yet set");
+  std::vector<double> flux((size_t)std::max(nl, 1) * std::max(nfr, 1));
+  return render_impl(c, iline0, nl, nfr, vmax_kms, dist_cm, flux.data(), imcir, cmask, tau_center, maserflag, nullptr,
+                     nullptr, false, ring_lo, ring_hi, ringsum);
 }
 
 int rl_render_rings_device(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, double dist_cm, int ring_lo,

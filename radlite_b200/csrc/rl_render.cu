@@ -2034,10 +2034,12 @@ __global__ void __launch_bounds__(256) wallprep_kernel(RenderParams P, double lw
   if (inv) atomicOr(&wstat[1], 1ull);
 }
 
+// one warp per ray: 32 segments at a time from the observer's end, the running optical depth and the running
+// smallest source function as warp scans
 __global__ void __launch_bounds__(128) wall_kernel(RenderParams P, const double *__restrict__ admin,
                                                    const double *__restrict__ smin,
                                                    const unsigned long long *__restrict__ wstat, int *nstart) {
-  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ray = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (ray >= P.nray) return;
   int ns = 1;
   const long long n0 = P.node_off[ray];
@@ -2064,22 +2066,43 @@ __global__ void __launch_bounds__(128) wall_kernel(RenderParams P, const double 
         sm = fmin(fmin(sm, __ldg(&smin[nd.cells.y])), fmin(__ldg(&smin[nd.cells.z]), __ldg(&smin[nd.cells.w])));
       }
     };
-    double cum = 0.0, a1, sfront;
-    at(N - 1, a1, sfront);
-    for (int n = N - 1; n >= 2; n--) {  // segment n joins nodes n-1 and n
-      double a0, s0;
-      at(n - 1, a0, s0);
-      sfront = fmin(sfront, s0);
-      cum += 0.5 * __ldg(&rec[n].ds) * (a0 + a1);
-      if (!(sfront > 0.0)) break;  // no emission bound in front: the ray keeps its full length
-      if (cum > P.wall_tau && cum - (lsmax - log(sfront)) > P.wall_tau) {
-        ns = n;
+    double cum0 = 0.0, sfront0;  // optical depth / smallest source function of everything in front of the chunk
+    {
+      double a;
+      at(N - 1, a, sfront0);
+    }
+    for (int top = N - 1; top >= 2; top -= 32) {  // lane j: segment n = top - j, joining nodes n-1 and n
+      const int n = top - lane;
+      double dtau = 0.0, sm = 1.0e300;
+      if (n >= 2) {
+        double a0, a1, s1;
+        at(n, a1, s1);
+        at(n - 1, a0, sm);
+        dtau = 0.5 * __ldg(&rec[n].ds) * (a0 + a1);
+      }
+      double cum = dtau, sf = sm;
+      for (int o = 1; o < 32; o <<= 1) {  // inclusive scans over the lanes (= towards the far end of the ray)
+        const double c = __shfl_up_sync(0xffffffffu, cum, o), m = __shfl_up_sync(0xffffffffu, sf, o);
+        if (lane >= o) {
+          cum += c;
+          sf = fmin(sf, m);
+        }
+      }
+      cum += cum0;
+      sf = fmin(sf, sfront0);
+      const bool dark = n >= 2 && !(sf > 0.0);  // no emission bound in front: the ray keeps its full length
+      const bool hit = n >= 2 && !dark && cum > P.wall_tau && cum - (lsmax - log(sf)) > P.wall_tau;
+      const unsigned stop = __ballot_sync(0xffffffffu, dark || hit);
+      if (stop) {
+        const int j = __ffs(stop) - 1;
+        if ((__ballot_sync(0xffffffffu, hit) >> j) & 1u) ns = top - j;
         break;
       }
-      a1 = a0;
+      cum0 = __shfl_sync(0xffffffffu, cum, 31);
+      sfront0 = __shfl_sync(0xffffffffu, sf, 31);
     }
   }
-  nstart[ray] = ns;
+  if (lane == 0) nstart[ray] = ns;
 }
 
 // The element integrations of the sub-gridded segments that the opaque-wall start skips, added to the E
@@ -2535,7 +2558,7 @@ void launch_span(const RenderParams &P, cudaStream_t st) {
 void launch_wall(const RenderParams &P, double lw_min, double *admin, double *smin, unsigned long long *wstat,
                  int *nstart, cudaStream_t st) {
   wallprep_kernel<<<(unsigned)((P.ncell + 255) / 256), 256, 0, st>>>(P, lw_min, admin, smin, wstat);
-  wall_kernel<<<(P.nray + 127) / 128, 128, 0, st>>>(P, admin, smin, wstat, nstart);
+  wall_kernel<<<(P.nray + 3) / 4, 128, 0, st>>>(P, admin, smin, wstat, nstart);
   if (P.subgrid)
     wallcount_kernel<<<P.nray, 128, (P.nfr + 1) * sizeof(unsigned), st>>>(P, nstart, P.use_z ? 0 : 1);
 }
