@@ -626,15 +626,22 @@ __device__ __forceinline__ void step_onediv(double alp0, double src0, double alp
   qv = (dtau > (double)1e-9f) ? fmin(qv, theomax) : theomax;
 }
 
-// sub-gridded segment in the staged (cN, kk) form (line.F:4745-4833); reference-ordered arithmetic
+__shared__ double s_T1[kTabN];       // 2^(j/kTabN): the exp table every integrate kernel fills at block start
+
+// sub-gridded segment in the staged (cN, kk) form (line.F:4745-4833): the sub-points and their order are the
+// reference's; each sub-step uses the kernels' own exp (table + polynomial) and the one-division qdr_src_2 step,
+// like every other step of ztile_kernel / tile_kernel (a sub-gridded segment is up to 32 of them)
 __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch, double &inten, double ds,
                                          double sleft, double sright, double sd0, double ad0, double cN0,
                                          double kk0, double dv0, double sd1, double ad1, double cN1,
                                          double kk1, double dv1, double lw, double &srcl0, double &alpl0,
                                          int init) {
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
   const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
   const double aa = k_aa * (0.5 * (lw + lw));
   const double norm = 0.56419583546 / aa;
+  const double ias = kTabSqrtScale / aa;  // pre-scaled reciprocal Doppler width (gauss_tab's argument scale)
+  const double un = dnu_ch * ias, uv = nu0 * ias;
   double sp = 0.0, cN_p = cN0, kk_p = kk0, dv_p = dv0, sd_p = sd0, ad_p = ad0;
   int n = 0;
   for (int j = 1; j <= kLgNrMax + 1; j++) {
@@ -652,16 +659,18 @@ __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch,
       s = ds; cN_c = cN1; kk_c = kk1; dv_c = dv1; sd_c = sd1; ad_c = ad1;
     }
     if (init) {
-      const double u0 = (dnu_ch - nu0 * dv_p) / aa;
-      const double phi0 = norm * exp(-(u0 * u0));
+      const double phi0 = norm * gauss_tab(fma(-uv, dv_p, un), T1, 0);
       srcl0 = cN_p * phi0;
       alpl0 = kk_p * phi0;
       init = 0;
     }
-    const double u1 = (dnu_ch - nu0 * dv_c) / aa;
-    const double phi1 = norm * exp(-(u1 * u1));
+    const double phi1 = norm * gauss_tab(fma(-uv, dv_c, un), T1, 0);
     const double srcl1 = cN_c * phi1, alpl1 = kk_c * phi1;
-    inten = qdr_src_2(inten, sd_p + srcl0, ad_p + alpl0, sd_c + srcl1, ad_c + alpl1, s - sp);
+    const double src0 = sd_p + srcl0, alp0 = ad_p + alpl0, src1 = sd_c + srcl1, alp1 = ad_c + alpl1;
+    const double hds = 0.5 * (s - sp);
+    double x, q;
+    step_onediv(alp0, src0, alp1, src1, hds * (alp0 + alp1), hds * (src0 + src1), T1, x, q);
+    inten = fma(inten, x, q);
     srcl0 = srcl1;
     alpl0 = alpl1;
     n++;
@@ -672,7 +681,6 @@ __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch,
 
 // per-block tables and per-item metadata of tile_kernel (file scope: the out-of-line slow path uses
 // them too)
-__shared__ double s_T1[kTabN];       // 2^(j/kTabN)
 __shared__ int2 s_meta[128];      // {line slot, channel | cmask bit} of the thread's item
 __shared__ unsigned s_flags[128]; // maser | extra elements << 8 of the thread's item
 __shared__ double s_dnu[128];     // line_dnu of the thread's item
@@ -1294,13 +1302,13 @@ __device__ __noinline__ unsigned zflagged(double *Ic, const ZSeg &g, uint32_t fl
         alpl0 = g.v0.kk * (g.nrm1 * e0);
       }
       const double src0 = g.v0.sd + srcl0, alp0 = g.v0.ad + alpl0;
-      const double r0 = div_fast(src0, alp0);
       const double alpl1 = g.v1.kk * (g.nrm1 * ec);
       const double src1 = fma(g.v1.cN, g.nrm1 * ec, g.v1.sd), alp1 = g.v1.ad + alpl1;
       const double hds = 0.5 * ds;
       const double dtau = hds * (alp0 + alp1), theomax = hds * (src0 + src1);
-      double r1;
-      full_step(inten, alp0, r0, src1, alp1, r1, dtau, theomax, T1, 0);
+      double x, q;
+      step_onediv(alp0, src0, alp1, src1, dtau, theomax, T1, x, q);
+      inten = fma(inten, x, q);
       ms = alpl1 * ds < (double)(-0.01f);
     }
     if (ms) mb |= 1u << c;
