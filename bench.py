@@ -173,12 +173,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=200):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(index)], stdout=self.f,
+                                       "-lms", str(period_ms), "-i", str(index)], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -262,7 +262,7 @@ def run_gpu(args):
             step_device()
         g.reset_counters()
         l0 = g.launch_count()
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(local, args.clock_ms)
         barrier()
         t0 = time.perf_counter()
         ms = np.zeros(5)
@@ -342,7 +342,7 @@ def run_gpu(args):
                 lo, hi = blocks[rank]
         g.reset_counters()
         l0 = g.launch_count()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local, args.clock_ms) if rank == 0 else None
         barrier()
         t0 = time.perf_counter()
         ms = np.zeros(5)
@@ -412,7 +412,8 @@ def run_gpu(args):
         lb = min(nl, 128)
         kernel = ("ztile_kernel<9> (one warp = one ray x 16 lines across the lanes x 18 channels) + zcont_kernel "
                   "(continuum-only ray x line pairs) + center_kernel" if lb >= 8 else
-                  "tile_kernel (block = one ray x <=128 (line, channel) items, staging warp) + center_kernel")
+                  "chan_kernel (one warp = one ray x one line x its channels across the lanes, channel-independent part "
+                  "once per node) + center_kernel")
         cpu = None
         if world == 1 and not args.no_cpu:
             ncores = os.cpu_count() or 1
@@ -483,6 +484,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based)")
     ap.add_argument("--lines", type=int, default=None, help="override the number of lines of the spectrum")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--clock-ms", type=int, default=200, help="nvidia-smi sampling period during the timed region "
+                    "(B200_PROFILING.md recipe: 200 ms)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE line, the JSON result: anything libraries print there (NCCL's version

@@ -193,9 +193,10 @@ void rl_reset_counters(rl_ctx *ctx);
  * result); 0 integrates every segment.  R, E, S above keep counting the reference's work;
  * rl_get_executed returns the element integrations this library actually performed. */
 int rl_set_wall_tau(rl_ctx *ctx, double tau);
-/* Integrate kernel: 0 = chosen by regime (ztile_kernel + zcont_kernel from 8 lines per batch, tile_kernel
- * below), 1 = ztile_kernel, 2 = tile_kernel.  The kernels agree to ~1e-13; sharded renders that must be
- * bit-identical to an unsharded one pin the kernel. */
+/* Integrate kernel: 0 = chosen by regime (ztile_kernel + zcont_kernel from 8 lines per batch, chan_kernel
+ * below), 1 = ztile_kernel, 2 = tile_kernel, 3 = chan_kernel.  ztile_kernel and chan_kernel give the same bits,
+ * tile_kernel agrees with them to ~1e-13; sharded renders that must be bit-identical to an unsharded one pin
+ * the kernel. */
 int rl_set_kernel(rl_ctx *ctx, int mode);
 double rl_get_executed(const rl_ctx *ctx);
 

@@ -17,10 +17,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # RADLITE_B200_LIB selects a tuning variant built by `make variant` (development only)
 LIB_PATH = os.environ.get("RADLITE_B200_LIB") or os.path.join(_HERE, "libradlite_b200.so")
 _lib = None
-# integrate kernel every new Renderer is pinned to: "auto" (library default: by lines per batch), "z", "tile"
+# integrate kernel every new Renderer is pinned to: "auto" (library default: by lines per batch), "z", "tile", "chan"
 # (the GPU parity tests run every model under all three)
 DEFAULT_KERNEL = "auto"
-_KERNEL_MODES = {"auto": 0, "z": 1, "tile": 2}
+_KERNEL_MODES = {"auto": 0, "z": 1, "tile": 2, "chan": 3}
 
 
 def load_library() -> C.CDLL:
@@ -79,7 +79,8 @@ class Renderer(Binding):
             self.set_kernel(DEFAULT_KERNEL)
 
     def set_kernel(self, mode: str):
-        """Pin the integrate kernel: "auto", "z" (ztile_kernel + zcont_kernel) or "tile" (tile_kernel)."""
+        """Pin the integrate kernel: "auto", "z" (ztile_kernel + zcont_kernel), "tile" (tile_kernel) or "chan"
+        (chan_kernel + zcont_kernel)."""
         self.lib.rl_set_kernel.argtypes = [C.c_void_p, C.c_int]
         self.lib.rl_set_kernel.restype = C.c_int
         self._check(self.lib.rl_set_kernel(self.ctx, _KERNEL_MODES[mode]))

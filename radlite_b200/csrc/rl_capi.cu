@@ -151,6 +151,7 @@ struct rl_ctx {
   DevBuf<int> d_status;
   // render buffers
   DevBuf<double4> d_cellL;
+  DevBuf<double2> d_cellD;
   DevBuf<LineDev> d_lines;
   DevBuf<double> d_line_dnu, d_velo, d_velz, d_star_line, d_isrf_line;
   DevBuf<int> d_lev_up, d_lev_down, d_inudust;
@@ -817,6 +818,7 @@ static int upload_line_tables(rl_ctx *c, int il0, int nb, int nfr, double vmax_k
     CU(c->d_ld_alp.upload(c->h_ld_alp.data() + off, (size_t)nb * ncell, c->st));
   }
   CU(c->d_cellL.ensure((size_t)nb * ncell));
+  CU(c->d_cellD.ensure((size_t)nb * ncell));
   return 0;
 }
 
@@ -849,6 +851,7 @@ static void run_prep(rl_ctx *c, int nb) {
   Q.ld_src = c->d_ld_src.p;
   Q.ld_alp = c->d_ld_alp.p;
   Q.cellL = c->d_cellL.p;
+  Q.cellD = c->d_cellD.p;
   launch_prep(Q, c->st);
   c->launches++;
 }
@@ -980,6 +983,7 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.node_off = c->d_node_off.p;
     P.nodes = nodes_dev(c);
     P.cellL = c->d_cellL.p;
+    P.cellD = c->d_cellD.p;
     P.ncell = (long long)ncell;
     P.lines = c->d_lines.p;
     P.line_dnu = c->d_line_dnu.p;
@@ -1000,17 +1004,21 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.tile_max_lines = tile_max_lines(tile_threads);
     P.tiles = nullptr;
     // integrate kernel by regime: with several lines per batch the lanes of a warp take lines and share
-    // the line-independent profile (ztile_kernel); single-line renders (BASELINE configs 1, 3) spread
-    // (line, channel) items over the threads of a block fed by a staging warp (tile_kernel).
-    // rl_set_kernel forces one of them (parity tests run both on every model).
-    P.use_z = (nb >= 8 && nfr <= 65535) ? 1 : 0;  // (ZTile carries channel numbers as 16-bit fields)
+    // the line-independent profile (ztile_kernel); renders of few lines (BASELINE configs 1, 3: one) put the
+    // channels of one line across the lanes, the channel-independent part computed once per node
+    // (chan_kernel).  tile_kernel ((line, channel) items over the threads of a block fed by a staging warp)
+    // remains for passbands of more than 65535 channels and as a cross-check.
+    // rl_set_kernel forces one of them (parity tests run all three on every model).
+    P.use_z = nfr <= 65535 ? 1 : 0;  // (ZTile carries channel numbers as 16-bit fields)
+    P.zlw = nb >= 8 ? 16 : 1;        // lines per tile; 1: chan_kernel
     if (c->kernel_mode == 2) P.use_z = 0;
-    else if (c->kernel_mode == 1 && nfr <= 65535) P.use_z = 1;
-    P.zlw = 16;
+    else if (c->kernel_mode == 1) P.zlw = 16;
+    else if (c->kernel_mode == 3) P.zlw = 1;
 #ifdef RL_TUNING_ENV
     if (const char *e = getenv("RL_KERNEL")) {
       if (!strcmp(e, "tile")) P.use_z = 0;
-      else if (!strcmp(e, "z") && nfr <= 65535) P.use_z = 1;
+      else if (!strcmp(e, "z") && nfr <= 65535) { P.use_z = 1; P.zlw = 16; }
+      else if (!strcmp(e, "chan") && nfr <= 65535) { P.use_z = 1; P.zlw = 1; }
     }
     if (const char *e = getenv("RL_ZLW")) P.zlw = atoi(e);
 #endif
@@ -1352,6 +1360,7 @@ int rl_render_rect(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, doub
     P.node_off = c->d_node_off.p;
     P.nodes = nodes_dev(c);
     P.cellL = c->d_cellL.p;
+    P.cellD = c->d_cellD.p;
     P.ncell = (long long)ncell;
     P.lines = c->d_lines.p;
     P.line_dnu = c->d_line_dnu.p;
@@ -1425,7 +1434,7 @@ double rl_get_executed(const rl_ctx *cc) {
   return (double)h;
 }
 int rl_set_kernel(rl_ctx *c, int mode) {
-  if (!c || mode < 0 || mode > 2) return 13;
+  if (!c || mode < 0 || mode > 3) return 13;
   c->kernel_mode = mode;
   return 0;
 }

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) prep_cells_kernel(PrepParams P) {
   o.z = pp[P.lev_up[l] - 1] * ab * rh * P.molpg;
   o.w = pp[P.lev_down[l] - 1] * ab * rh * P.molpg;
   P.cellL[(size_t)cell * P.nl + l] = o;
+  P.cellD[(size_t)cell * P.nl + l] = make_double2(src, alp);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -628,9 +629,42 @@ __device__ __forceinline__ void step_onediv(double alp0, double src0, double alp
 
 __shared__ double s_T1[kTabN];       // 2^(j/kTabN): the exp table every integrate kernel fills at block start
 
-// sub-gridded segment in the staged (cN, kk) form (line.F:4745-4833): the sub-points and their order are the
+// Sub-gridded segment in the staged (cN, kk) form (line.F:4745-4833): the sub-points and their order are the
 // reference's; each sub-step uses the kernels' own exp (table + polynomial) and the one-division qdr_src_2 step,
-// like every other step of ztile_kernel / tile_kernel (a sub-gridded segment is up to 32 of them)
+// like every other step of the integrate kernels (a sub-gridded segment is up to 32 of them).  sub_point is
+// the one place a sub-point is evaluated.
+struct SubCtx {
+  double ds, sd0, ad0, cN0, kk0, dv0, sd1, ad1, cN1, kk1, dv1;
+  double un, uv, norm;  // dnu and nu0 times the scaled reciprocal Doppler width ; profile norm
+};
+__device__ __forceinline__ SubCtx sub_ctx(double nu0, double k_aa, double dnu_ch, double ds, double sd0, double ad0,
+                                          double cN0, double kk0, double dv0, double sd1, double ad1, double cN1,
+                                          double kk1, double dv1, double lw) {
+  SubCtx k;
+  k.ds = ds;
+  k.sd0 = sd0; k.ad0 = ad0; k.cN0 = cN0; k.kk0 = kk0; k.dv0 = dv0;
+  k.sd1 = sd1; k.ad1 = ad1; k.cN1 = cN1; k.kk1 = kk1; k.dv1 = dv1;
+  const double aa = k_aa * (0.5 * (lw + lw));
+  k.norm = 0.56419583546 / aa;
+  const double ias = kTabSqrtScale / aa;  // pre-scaled reciprocal Doppler width (gauss_tab's argument scale)
+  k.un = dnu_ch * ias;
+  k.uv = nu0 * ias;
+  return k;
+}
+__device__ __forceinline__ double lerp_rn(double a, double b, double w, double w1);
+// dust pair and line terms at distance s from the segment's start node (endpoint: the end node itself)
+__device__ __forceinline__ void sub_point(const SubCtx &k, double s, bool endpoint, uint32_t T1, double &sd,
+                                          double &ad, double &srcl, double &alpl) {
+  const double eps = s / k.ds, epsp = 1.0 - eps;
+  const double cN = endpoint ? k.cN1 : lerp_rn(k.cN0, k.cN1, eps, epsp);
+  const double kk = endpoint ? k.kk1 : lerp_rn(k.kk0, k.kk1, eps, epsp);
+  const double dv = endpoint ? k.dv1 : lerp_rn(k.dv0, k.dv1, eps, epsp);
+  sd = endpoint ? k.sd1 : lerp_rn(k.sd0, k.sd1, eps, epsp);
+  ad = endpoint ? k.ad1 : lerp_rn(k.ad0, k.ad1, eps, epsp);
+  const double phi = k.norm * gauss_tab(fma(-k.uv, dv, k.un), T1, 0);
+  srcl = cN * phi;
+  alpl = kk * phi;
+}
 __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch, double &inten, double ds,
                                          double sleft, double sright, double sd0, double ad0, double cN0,
                                          double kk0, double dv0, double sd1, double ad1, double cN1,
@@ -638,34 +672,29 @@ __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch,
                                          int init) {
   const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
   const double lg_ds = (sright - sleft) / (kLgNrMax - 1.0);
-  const double aa = k_aa * (0.5 * (lw + lw));
-  const double norm = 0.56419583546 / aa;
-  const double ias = kTabSqrtScale / aa;  // pre-scaled reciprocal Doppler width (gauss_tab's argument scale)
-  const double un = dnu_ch * ias, uv = nu0 * ias;
-  double sp = 0.0, cN_p = cN0, kk_p = kk0, dv_p = dv0, sd_p = sd0, ad_p = ad0;
-  int n = 0;
-  for (int j = 1; j <= kLgNrMax + 1; j++) {
-    double s, cN_c, kk_c, dv_c, sd_c, ad_c;
-    if (j <= kLgNrMax) {
-      s = sleft + (j - 1) * lg_ds;
-      if (!(s > 0.0 && s < ds)) continue;
-      const double eps = s / ds, epsp = 1.0 - eps;
-      cN_c = epsp * cN0 + eps * cN1;
-      kk_c = epsp * kk0 + eps * kk1;
-      dv_c = epsp * dv0 + eps * dv1;
-      sd_c = epsp * sd0 + eps * sd1;
-      ad_c = epsp * ad0 + eps * ad1;
-    } else {
-      s = ds; cN_c = cN1; kk_c = kk1; dv_c = dv1; sd_c = sd1; ad_c = ad1;
-    }
-    if (init) {
-      const double phi0 = norm * gauss_tab(fma(-uv, dv_p, un), T1, 0);
-      srcl0 = cN_p * phi0;
-      alpl0 = kk_p * phi0;
-      init = 0;
-    }
-    const double phi1 = norm * gauss_tab(fma(-uv, dv_c, un), T1, 0);
-    const double srcl1 = cN_c * phi1, alpl1 = kk_c * phi1;
+  const SubCtx k = sub_ctx(nu0, k_aa, dnu_ch, ds, sd0, ad0, cN0, kk0, dv0, sd1, ad1, cN1, kk1, dv1, lw);
+  if (init) {  // the start point with this segment's width (line.F:4559-4586)
+    const double phi0 = k.norm * gauss_tab(fma(-k.uv, dv0, k.un), T1, 0);
+    srcl0 = cN0 * phi0;
+    alpl0 = kk0 * phi0;
+  }
+  // which of the 31 sub-points lie inside the segment: a run jlo .. jlo+cnt-1 (s grows with j).  Found by a
+  // branch-free scan, so that the lanes of a warp then walk THEIR sub-points in step (k-th point of every lane
+  // together) instead of all 31 indices with the lanes whose point is outside idling
+  int jlo = 0, cnt = 0;
+#pragma unroll 1
+  for (int j = 1; j <= kLgNrMax; j++) {
+    const double s = fma((double)(j - 1), lg_ds, sleft);
+    const bool in = s > 0.0 && s < ds;
+    jlo = (in && cnt == 0) ? j : jlo;
+    cnt += in ? 1 : 0;
+  }
+  double sp = 0.0, sd_p = sd0, ad_p = ad0;
+  for (int kk = 0; kk <= cnt; kk++) {
+    const bool endpoint = kk == cnt;
+    const double s = endpoint ? ds : fma((double)(jlo + kk - 1), lg_ds, sleft);
+    double sd_c, ad_c, srcl1, alpl1;
+    sub_point(k, s, endpoint, T1, sd_c, ad_c, srcl1, alpl1);
     const double src0 = sd_p + srcl0, alp0 = ad_p + alpl0, src1 = sd_c + srcl1, alp1 = ad_c + alpl1;
     const double hds = 0.5 * (s - sp);
     double x, q;
@@ -673,12 +702,11 @@ __device__ __noinline__ int subgrid_tile(double nu0, double k_aa, double dnu_ch,
     inten = fma(inten, x, q);
     srcl0 = srcl1;
     alpl0 = alpl1;
-    n++;
-    sp = s; cN_p = cN_c; kk_p = kk_c; dv_p = dv_c; sd_p = sd_c; ad_p = ad_c;
+    sp = s; sd_p = sd_c; ad_p = ad_c;
   }
+  const int n = cnt + 1;
   return n;
 }
-
 // per-block tables and per-item metadata of tile_kernel (file scope: the out-of-line slow path uses
 // them too)
 __shared__ int2 s_meta[128];      // {line slot, channel | cmask bit} of the thread's item
@@ -1721,6 +1749,7 @@ __global__ void __launch_bounds__(32 * kZcWarps, RL_ZCMINB) zcont_kernel(const _
   double I = ns > 1 ? 0.0 : ((P.out_itype == 3) ? __ldg(&P.isrf_line[(size_t)l * P.nfr]) : __ldg(&Lp->i_outer));
   const NodeRec *__restrict__ rec = P.nodes.rec + n0;
   const double4 *__restrict__ cl = P.cellL + l;
+  const double2 *__restrict__ cd = P.cellD + l;
   const uint32_t nl = (uint32_t)P.nl;
   const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
   ZCNode *sn = s_zc[warp];
@@ -1741,12 +1770,12 @@ __global__ void __launch_bounds__(32 * kZcWarps, RL_ZCMINB) zcont_kernel(const _
   auto dust_at = [&](const ZCNode *x) {
     ZVal o;
     o.cN = o.kk = 0.0;
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(cl + x->offA));
-    const double2 b = __ldg(reinterpret_cast<const double2 *>(cl + x->offB));
+    const double2 a = __ldg(cd + x->offA);
+    const double2 b = __ldg(cd + x->offB);
     double2 r;
     if (x->icr == 3) {
-      const double2 c = __ldg(reinterpret_cast<const double2 *>(cl + x->offC));
-      const double2 d = __ldg(reinterpret_cast<const double2 *>(cl + x->offD));
+      const double2 c = __ldg(cd + x->offC);
+      const double2 d = __ldg(cd + x->offD);
       const double t1 = 1.0 - x->w, r1 = 1.0 - x->w2;
       r.x = lerp_rn(lerp_rn(a.x, b.x, x->w, t1), lerp_rn(c.x, d.x, x->w, t1), x->w2, r1);
       r.y = lerp_rn(lerp_rn(a.y, b.y, x->w, t1), lerp_rn(c.y, d.y, x->w, t1), x->w2, r1);
@@ -1837,10 +1866,10 @@ __global__ void __launch_bounds__(32 * kZcWarps, RL_ZCMINB) zcont_kernel(const _
           (x1->icr != 3) && (x1[1].icr != 3)) {
         // two dust-only segments at once (nodes s-1, s, s+1 carry no line terms)
         const ZCNode *x2 = x1 + 1;
-        const double2 a1 = __ldg(reinterpret_cast<const double2 *>(cl + x1->offA));
-        const double2 b1 = __ldg(reinterpret_cast<const double2 *>(cl + x1->offB));
-        const double2 a2 = __ldg(reinterpret_cast<const double2 *>(cl + x2->offA));
-        const double2 b2 = __ldg(reinterpret_cast<const double2 *>(cl + x2->offB));
+        const double2 a1 = __ldg(cd + x1->offA);
+        const double2 b1 = __ldg(cd + x1->offB);
+        const double2 a2 = __ldg(cd + x2->offA);
+        const double2 b2 = __ldg(cd + x2->offB);
         const double2 d1 = dust2(x1, a1, b1), d2 = dust2(x2, a2, b2);
         const double h1 = x1->hds, h2 = x2->hds;
         const double D1 = h1 * (v0.ad + d1.y), T1h = h1 * (v0.sd + d1.x);
@@ -1913,6 +1942,349 @@ __global__ void __launch_bounds__(32 * kZcWarps, RL_ZCMINB) zcont_kernel(const _
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// chan_kernel: the formal solution with the CHANNELS of one line across the lanes of a warp -- renders with
+// fewer than 8 lines per batch (BASELINE configs 1 and 3: one line, up to 199 channels per ray), where there
+// are no lines to put side by side and nothing to share between them.
+//
+// One warp = one ray x one line x up to 32 x kCCw consecutive channels (lane = channel, kCCw blocks of 32
+// channels per thread; intensity and the profile value at the previous node in registers); the tiles are
+// zplan_kernel's with one line per tile.  Everything that does not depend on the channel is the same for all
+// lanes, so it is computed ONCE per (ray, line, node) -- by the lanes acting as nodes: per batch of 31
+// segments lane k loads node record k, gathers and interpolates its stencil cells (the 32 gathers of a batch
+// in flight together), takes the previous node's values from lane k-1 and leaves in shared memory (CSeg)
+//   * the six constants of  dtau = D + P e0 + Q e1 ,  theomax = Th + R e0 + S e1  (e0, e1: profile at the
+//     two nodes),
+//   * the complete step  I <- I xd + qd  of a channel that sees no line at either node (e0 = e1 = 0: the
+//     dust-only segment, identical for all such channels).
+// The lanes then walk the batch as channels.  Per node and block of 32 channels: the profile argument
+// (v_k/c - Omega.v/c) / width (one FMA; formed in velocity like ztile_kernel's) tells whether the channel is
+// beyond the point where the kernels flush the profile to 0 (exp(-345)); if that holds for the whole block at
+// both nodes -- the rule in a cube, where a node's line covers a few of the ~200 channels -- the block takes
+// the staged dust-only step: one FMA per channel.  Otherwise one Gaussian per channel (table-based exp) and the
+// step; the case split of transfer.F:1517,1542 needs no vote at the node level (D + |P| + |Q| <= 1e-9 is a
+// property of the node: CSeg.thin), and where every opacity of the two nodes is positive (CSeg.upos, a
+// property of the node as well) qdr_src_2's selections on the sign of the opacities drop out.  The arithmetic
+// per (ray, line, channel) is that of ztile_kernel (same functions, same operation order): the two kernels
+// give the same bits.  Flagged nodes (first segment, inner hole / star mixing, 6q > 1 sub-grid candidates)
+// go through chan_flagged, out of line.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) CSeg {  // segment ending at a staged node
+  double D, Th, Pq, Q, R, S;
+  double ian, dvi;           // scaled reciprocal Doppler width of the segment ; Omega.v/c at its end node times it
+  double xd, qd;             // the dust-only step of this segment
+  uint32_t fl, thin, neg, upos;
+};
+struct __align__(16) CNode {  // staged node
+  double sd, ad, A1, K1;      // dust pair ; c_src N_up and kk, times the profile norm of the segment ending here
+  double cN, kk, nrm, lw;     // (flagged path) c_src N_up ; kk ; that norm ; line width
+  double dvmu, ds;
+};
+// Flagged segment of chan_kernel's line for the cw channel blocks of a thread (Ic, and the profile values epl /
+// ecl at the two nodes, in local memory): zflagged's arithmetic per channel.  Returns the maser bits; xtra += the
+// extra element integrations of sub-gridded channels.
+__device__ __noinline__ unsigned chan_flagged(double *Ic, const double *epl, const double *ecl, const ZSeg &g,
+                                              uint32_t fl, int cw, const LineDev *__restrict__ L,
+                                              const double *__restrict__ dnu_l, const double *__restrict__ star_l,
+                                              const double *__restrict__ velo, int jb, int jmax, int cmin,
+                                              double starfract, unsigned realbits, unsigned &xtra) {
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
+  const double nu0 = __ldg(&L->nu0), k_aa = __ldg(&L->k_aa), inv_nu0 = __ldg(&L->inv_nu0);
+  const double ds = g.ds;
+  const int init = (fl & (kFlagInit | kFlagStar | kFlagZero)) ? 1 : 0;
+  unsigned mb = 0;
+  for (int c = 0; c < cw; c++) {
+    const int j = min(jb + c * 32, jmax);
+    const int ch = j ? cmin + j - 1 : 0;
+    const double dnu = __ldg(dnu_l + ch);
+    const double ep = epl[c], ec = ecl[c];
+    double inten = Ic[c];
+    if (fl & kFlagZero) inten = 0.0;
+    if (fl & kFlagStar) inten = (1.0 - starfract) * inten + starfract * __ldg(star_l + ch);
+    double srcl0 = g.v0.cN * (g.nrm0 * ep), alpl0 = g.v0.kk * (g.nrm0 * ep);  // carried state (line.F:4613-4615)
+    bool need = false, ms = false;
+    double sleft = 0.0, sright = 0.0;
+    if (fl & kFlagSub) {  // line.F:4706-4745
+      const double q = fabs((g.dv1 - g.dv0) / (g.lwav / 2.99792458e5));
+      const double s_c = ds * (dnu * inv_nu0 - g.dv0) / (g.dv1 - g.dv0);
+      const double dls3 = 3.0 * (ds / q);
+      sright = s_c + dls3;
+      sleft = s_c - dls3;
+      need = sright > 0.0 && sleft < ds;
+    }
+    if (!need) {
+      if (init) {  // line.F:4559-4586: the start point with this segment's width
+        const double vel = __ldg(velo + ch);
+        const double e0 = gauss_tab(fma(vel, g.ian, -(g.dv0 * g.ian)), T1, 0);
+        srcl0 = g.v0.cN * (g.nrm1 * e0);
+        alpl0 = g.v0.kk * (g.nrm1 * e0);
+      }
+      const double src0 = g.v0.sd + srcl0, alp0 = g.v0.ad + alpl0;
+      const double alpl1 = g.v1.kk * (g.nrm1 * ec);
+      const double src1 = fma(g.v1.cN, g.nrm1 * ec, g.v1.sd), alp1 = g.v1.ad + alpl1;
+      const double hds = 0.5 * ds;
+      const double dtau = hds * (alp0 + alp1), theomax = hds * (src0 + src1);
+      double x, q;
+      step_onediv(alp0, src0, alp1, src1, dtau, theomax, T1, x, q);
+      inten = fma(inten, x, q);
+      ms = alpl1 * ds < (double)(-0.01f);
+    }
+    else {
+      const int n = subgrid_tile(nu0, k_aa, dnu, inten, ds, sleft, sright, g.v0.sd, g.v0.ad, g.v0.cN, g.v0.kk, g.dv0,
+                                 g.v1.sd, g.v1.ad, g.v1.cN, g.v1.kk, g.dv1, g.lwav, srcl0, alpl0, init);
+      ms = alpl0 * ds < (double)(-0.01f);
+      if ((realbits >> c) & 1u) xtra += (unsigned)(n - 1);
+    }
+    if (ms) mb |= 1u << c;
+    Ic[c] = inten;
+  }
+  return mb;
+}
+
+#ifndef RL_CCW
+#define RL_CCW 3
+#endif
+constexpr int kCCw = RL_CCW;  // blocks of 32 channels per chan_kernel thread
+#ifndef RL_CMINB
+#define RL_CMINB 24  // resident blocks (= warps) per SM the register budget is set for
+#endif
+template <int CW>
+__global__ void __launch_bounds__(32, RL_CMINB) chan_kernel(const __grid_constant__ RenderParams P) {
+  __shared__ CSeg s_seg[32];
+  __shared__ CNode s_cn[32];
+  const int lane = threadIdx.x;
+  if (lane < kTabN) s_T1[lane] = exp2((double)lane * (1.0 / kTabN));
+  __syncwarp();
+  const unsigned tix = blockIdx.x;
+  if (tix >= P.nztile) return;
+  const ZTile t = P.ztiles[tix];
+  const int ray = t.ray;
+  const int l = (int)P.zlines[t.loff];
+  const int nchk = t.nchk, j0 = t.j0, cmin = t.cmin;
+  const int cw = (nchk + 31) >> 5;  // channel blocks in use
+  const int jmax = j0 + nchk - 1, jb = j0 + lane;
+  // channel of my slot c: position min(jb + 32 c, jmax) of the list {0, cmin, cmin + 1, ...}
+  auto chan_of = [&](int c) {
+    const int j = min(jb + c * 32, jmax);
+    return j ? cmin + j - 1 : 0;
+  };
+  const int4 rg = P.rng[(long long)ray * P.nl + l];
+  unsigned realbits = 0;  // slots that are channels the reference integrates for this line
+#pragma unroll
+  for (int c = 0; c < CW; c++) {
+    if (c * 32 + lane < nchk) {
+      const int ch = chan_of(c);
+      if (ch == 0 || (ch >= rg.x && ch <= rg.y) || ch == rg.z) realbits |= 1u << c;
+    }
+  }
+  const LineDev *Lp = P.lines + l;
+  const double c_src = __ldg(&Lp->c_src);
+  const double cb_du = __ldg(&Lp->c_alp) * __ldg(&Lp->bdu), cb_ud = __ldg(&Lp->c_alp) * __ldg(&Lp->bud);
+  const double knorm = 0.56419583546 / __ldg(&Lp->k_aa);
+  double I[CW], ep[CW], vel[CW];
+#pragma unroll
+  for (int c = 0; c < CW; c++) {
+    const int ch = chan_of(c);
+    I[c] = (P.out_itype == 3) ? __ldg(&P.isrf_line[(size_t)l * P.nfr + ch]) : __ldg(&Lp->i_outer);
+    vel[c] = __ldg(P.velz + ch);
+    ep[c] = 0.0;
+  }
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
+  const long long n0 = P.node_off[ray];
+  const int N = (int)(P.node_off[ray + 1] - n0);
+  const NodeRec *__restrict__ rec = P.nodes.rec + n0;
+  const double4 *__restrict__ cl = P.cellL + l;
+  const size_t nl = (size_t)P.nl;
+  // first segment to integrate: everything before it lies behind an opaque dust wall (wall_kernel)
+  const int ns = P.nstart ? max(1, min(__ldg(&P.nstart[ray]), N - 1)) : 1;
+  if (ns > 1) {
+#pragma unroll
+    for (int c = 0; c < CW; c++) I[c] = 0.0;
+  }
+  unsigned mbits = 0, xtra = 0;
+  constexpr long long kThin = 0x3E112E0BE0000000LL;  // bit pattern of (double)1e-9f (transfer.F:1542, REAL literal)
+
+  for (int c0 = ns; c0 < N; c0 += 31) {
+    const int cnt = min(31, N - c0);
+    __syncwarp();  // the previous batch is consumed
+    {  // lanes as nodes c0-1 .. c0+cnt-1
+      ZVal v;
+      v.sd = v.ad = v.cN = v.kk = 0.0;
+      double nrm = 0.0, hds = 0.0, ian = 0.0, dvi = 0.0, lw = 0.0, dvmu = 0.0, ds = 0.0;
+      uint32_t fl = 0;
+      if (lane <= cnt) {
+        const int node = c0 - 1 + lane;
+        const double2 *p = reinterpret_cast<const double2 *>(rec + node);
+        const double2 a = __ldg(p), b = __ldg(p + 1), w = __ldg(p + 2);
+        const int4 cells = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        const uint32_t icr = ((uint32_t)cells.x >> kCellFlagShift) & kFlagIcrMask;
+        const double4 ca = ldg4(cl + (size_t)(cells.x & kCellMask) * nl);
+        const double4 cb = ldg4(cl + (size_t)(icr == 2 ? cells.z : cells.y) * nl);
+        double4 iv;
+        if (icr == 3) {
+          const double4 cc = ldg4(cl + (size_t)cells.z * nl), cd = ldg4(cl + (size_t)cells.w * nl);
+          iv = interp4(ca, cb, cc, cd, w.x, w.y);
+        } else {
+          iv = interp2(ca, cb, icr == 2 ? w.x : w.y);
+        }
+        v = zvals(iv, c_src, cb_du, cb_ud);
+        fl = ((uint32_t)cells.x >> kCellFlagShift) & ~kFlagIcrMask;
+        if (!P.subgrid) fl &= ~kFlagSub;
+        if (node == 1) fl |= kFlagInit;  // first segment of the ray: nothing carried yet
+        ds = a.x;
+        dvmu = a.y;
+        lw = b.x;
+        hds = 0.5 * ds;
+        nrm = knorm * b.y;
+        ian = b.y * kIanScale;
+        dvi = dvmu * ian;
+      }
+      ZVal v0;
+      v0.sd = __shfl_up_sync(0xffffffffu, v.sd, 1);
+      v0.ad = __shfl_up_sync(0xffffffffu, v.ad, 1);
+      v0.cN = __shfl_up_sync(0xffffffffu, v.cN, 1);
+      v0.kk = __shfl_up_sync(0xffffffffu, v.kk, 1);
+      const double nrm0 = __shfl_up_sync(0xffffffffu, nrm, 1);
+      if (lane <= cnt) {
+        CNode n;
+        n.sd = v.sd; n.ad = v.ad; n.A1 = v.cN * nrm; n.K1 = v.kk * nrm;
+        n.cN = v.cN; n.kk = v.kk; n.nrm = nrm; n.lw = lw;
+        n.dvmu = dvmu; n.ds = ds;
+        s_cn[lane] = n;
+        CSeg g;
+        const double hn0 = hds * nrm0, hn1 = hds * nrm;
+        g.D = hds * (v0.ad + v.ad);
+        g.Th = hds * (v0.sd + v.sd);
+        g.Pq = hn0 * v0.kk;
+        g.Q = hn1 * v.kk;
+        g.R = hn0 * v0.cN;
+        g.S = hn1 * v.cN;
+        g.ian = ian;
+        g.dvi = dvi;
+        step_onediv(v0.ad, v0.sd, v.ad, v.sd, g.D, g.Th, T1, g.xd, g.qd);
+        g.fl = fl;
+        g.neg = v.kk < 0.0 ? 1u : 0u;  // inverted populations: full path, which carries the maser test
+        g.thin = (!g.neg && !(__double_as_longlong(g.D + fabs(g.Pq) + fabs(g.Q)) > kThin)) ? 1u : 0u;
+        // every opacity of the segment is positive whatever the profile (it is >= 0): dust opacity positive
+        // at both nodes, no inversion at either
+        g.upos = (!g.neg && v0.ad > kAlpMin && v.ad > kAlpMin && !(v0.kk * nrm0 < 0.0)) ? 1u : 0u;
+        s_seg[lane] = g;
+      }
+    }
+    __syncwarp();
+    if (c0 == ns) {  // profile at the node the first integrated segment starts from (with its own width)
+      const double ian = s_seg[0].ian, dvi = s_seg[0].dvi;
+#pragma unroll
+      for (int c = 0; c < CW; c++) ep[c] = gauss_tab(fma(vel[c], ian, -dvi), T1, 0);
+    }
+    for (int s = 1; s <= cnt; s++) {
+      const CSeg *g = s_seg + s;
+      const uint32_t fl = g->fl;
+      const double ian = g->ian, dvi = g->dvi;
+      if (fl == 0) {
+#pragma unroll
+        for (int c = 0; c < CW; c++) {
+          if (c < cw) {
+            const double u = fma(vel[c], ian, -dvi);
+            const bool nolin = (((unsigned)__double2hiint(u) & 0x7fffffffu) > kHiUmax) & (ep[c] == 0.0);
+            if (__all_sync(0xffffffffu, nolin)) {
+              I[c] = fma(I[c], g->xd, g->qd);  // (the profile stays 0)
+            } else {
+              const double ec = gauss_tab(u, T1, 0);
+              const double dtau = fma(g->Pq, ep[c], fma(g->Q, ec, g->D));
+              const double theo = fma(g->R, ep[c], fma(g->S, ec, g->Th));
+              if (g->thin || !__any_sync(0xffffffffu, __double_as_longlong(dtau) > kThin)) {
+                // transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau
+                I[c] = fma(I[c], 1.0 - dtau, theo);
+              } else {
+                const CNode *n0p = s_cn + (s - 1), *n1p = s_cn + s;
+                const double alp1 = fma(n1p->K1, ec, n1p->ad), src1 = fma(n1p->A1, ec, n1p->sd);
+                const double alp0 = fma(n0p->K1, ep[c], n0p->ad), src0 = fma(n0p->A1, ep[c], n0p->sd);
+                double x, q;
+                if (g->upos) {
+                  // step_onediv with both opacities known to be positive
+                  const double xpe = expneg_tab(dtau, T1, 0);
+                  const double e0 = 1.0 - xpe, e1 = dtau - e0;
+                  const bool thick = dtau > 1.e-6;
+                  const double hb = 0.5 * dtau;
+                  const double ca = thick ? fma(e0, dtau, -e1) : hb, cb = thick ? e1 : hb, dd = thick ? dtau : 1.0;
+                  const double den = dd * (alp0 * alp1);
+                  const double num = fma(ca, src0 * alp1, cb * (src1 * alp0));
+                  x = thick ? xpe : (1.0 - dtau);
+                  q = div_fast(num, den);
+                  q = (dtau > (double)1e-9f) ? fmin(q, theo) : theo;
+                } else {
+                  step_onediv(alp0, src0, alp1, src1, dtau, theo, T1, x, q);
+                  if (g->neg && (n1p->K1 * ec) * n1p->ds < (double)(-0.01f)) mbits |= 1u << c;  // telescope.F:4295
+                }
+                I[c] = fma(I[c], x, q);
+              }
+              ep[c] = ec;
+            }
+          }
+        }
+      } else {
+        double tmp[CW], epl[CW], ecl[CW];
+#pragma unroll
+        for (int c = 0; c < CW; c++) {
+          tmp[c] = I[c];
+          epl[c] = ep[c];
+          ecl[c] = gauss_tab(fma(vel[c], ian, -dvi), T1, 0);
+        }
+        const CNode *n0p = s_cn + (s - 1), *n1p = s_cn + s;
+        ZSeg sg;
+        sg.ds = n1p->ds;
+        sg.lwav = 0.5 * (n0p->lw + n1p->lw);
+        sg.dv0 = n0p->dvmu;
+        sg.dv1 = n1p->dvmu;
+        sg.ian = ian;
+        sg.nrm0 = n0p->nrm;
+        sg.nrm1 = n1p->nrm;
+        sg.v0.sd = n0p->sd; sg.v0.ad = n0p->ad; sg.v0.cN = n0p->cN; sg.v0.kk = n0p->kk;
+        sg.v1.sd = n1p->sd; sg.v1.ad = n1p->ad; sg.v1.cN = n1p->cN; sg.v1.kk = n1p->kk;
+        mbits |= chan_flagged(tmp, epl, ecl, sg, fl, cw, Lp, P.line_dnu + (size_t)l * P.nfr,
+                              P.star_line + (size_t)l * P.nfr, P.velz, jb, jmax, cmin, P.starfract, realbits, xtra);
+#pragma unroll
+        for (int c = 0; c < CW; c++) {
+          I[c] = tmp[c];
+          ep[c] = ecl[c];
+        }
+      }
+    }
+  }
+  // results: only the slots that are channels the reference integrates for this line
+  unsigned long long r = 0;
+  const size_t row = (size_t)l * (size_t)(P.nrr + 1) * P.nphi + (size_t)img_row(P, ray);
+#pragma unroll
+  for (int c = 0; c < CW; c++) {
+    if ((realbits >> c) & 1u) {
+      const int ch = chan_of(c);
+      P.img[row * P.nfr + ch] = I[c];
+      if (P.sparse && I[c] == 0.0) P.dense[(long long)ray * P.nl + l] = 2;  // see fill_sparse_kernel
+      if (P.integ) {
+        const bool masked = P.nonredundant ? (ch != rg.z) : (ch == 0);  // telescope.F:548,575
+        P.integ[row * P.nfr + ch] = masked ? 1 : 2;
+      }
+      r++;
+    }
+  }
+  if (mbits & realbits) atomicOr(&P.maser[l], 1);
+  unsigned long long sct = r * (unsigned long long)(N > 0 ? N - 1 : 0), e = sct + xtra;
+  unsigned long long ex = r * (unsigned long long)(N > ns ? N - ns : 0) + xtra;
+  for (int o = 16; o; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    sct += __shfl_xor_sync(0xffffffffu, sct, o);
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  if (lane == 0 && r) {
+    atomicAdd(&P.counters[0], r);
+    atomicAdd(&P.counters[1], e);
+    atomicAdd(&P.counters[2], sct);
+    atomicAdd(&P.counters[3], ex);
+  }
+}
+
 // tiles of ztile_kernel, one thread per ray.  The lines that carry a channel window on this ray (in index
 // order, compacted into zlines) are cut into groups of zlw; the channel list of a group is
 // {0} + [min lo, max hi] over its lines (a superset of every line's own item channels -- the kernel
@@ -1935,7 +2307,7 @@ __global__ void zplan_kernel(RenderParams P) {
       const int nch = 1 + (cmax - cmin + 1);
       int lws = 0;
       while ((1 << lws) < cnt) lws++;
-      const int maxch = (32 >> lws) * kZCw;
+      const int maxch = (32 >> lws) * (P.zlw == 1 ? kCCw : kZCw);
       const int nchunk = (nch + maxch - 1) / maxch, per = (nch + nchunk - 1) / nchunk;
       for (int j0 = 0; j0 < nch; j0 += per) {
         if (FILL) {
@@ -1959,7 +2331,7 @@ __global__ void zplan_kernel(RenderParams P) {
     // pass 2: lines without a window whose channel 0 lies inside the ray's velocity span, so that their
     // first skipped channel is integrated as well (telescope.F:557-612; rare)
     for (int pass = 0; pass < 3; pass++) {
-      const int gsz = pass ? 32 : P.zlw;
+      const int gsz = (pass == 1 || P.zlw > 1 && pass == 2) ? 32 : P.zlw;  // (chan_kernel: one line per tile)
       int gstart = na, cmin = 0x7fffffff, cmax = -1;
       for (int l = 0; l < P.nl; l++) {
         if (!ni[l]) continue;
@@ -2617,7 +2989,8 @@ void launch_zcont(const RenderParams &P, unsigned tile0, unsigned ntile, cudaStr
 void launch_integrate(const RenderParams &P, unsigned total_ctas, cudaStream_t st) {
   if (!total_ctas) return;
   if (P.use_z) {
-    ztile_kernel<kZCw><<<(total_ctas + kZWarps - 1) / kZWarps, 32 * kZWarps, 0, st>>>(P);
+    if (P.zlw == 1) chan_kernel<kCCw><<<total_ctas, 32, 0, st>>>(P);
+    else ztile_kernel<kZCw><<<(total_ctas + kZWarps - 1) / kZWarps, 32 * kZWarps, 0, st>>>(P);
     return;
   }
   if (P.tile_threads == 128) tile_kernel<128><<<total_ctas, 128 + kProducerThreads, P.smem_budget, st>>>(P);

@@ -169,6 +169,8 @@ struct RenderParams {
   const long long *node_off;
   NodesDev nodes;
   const double4 *cellL;  // [ncell][nl] (cell-major: the lines of a tile at one cell are contiguous)
+  const double2 *cellD;  // [ncell][nl] the dust pair {src_dust, alp_dust} of cellL once more, compact: zcont_kernel's
+                         // dust-only gathers touch half the sectors
   long long ncell;
   const LineDev *lines;      // [nl]
   const double *line_dnu;    // [nl][nfr]
@@ -233,6 +235,7 @@ struct PrepParams {
   const double *ld_src;  // [nl][ncell]
   const double *ld_alp;
   double4 *cellL;        // [ncell][nl]
+  double2 *cellD;        // [ncell][nl] {src_dust, alp_dust}
 };
 
 }  // namespace rl

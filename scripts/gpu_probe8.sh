@@ -1,0 +1,7 @@
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_wall.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_cellD.json 2>/dev/null
+python -c "import json;d=json.load(open('gpurun_out/bench_cellD.json'));print('cfg 2:',round(d['ms_per_step'],2),'e2e',round(d['e2e']['ms_per_step'],2),{k:round(v,2) for k,v in d['phase_ms_per_step'].items()},round(d['roofline']['frac'],4))"
+for v in default c16 c24; do
+  L=A=1; if [ "$v" != "default" ]; then L=RADLITE_B200_LIB=$PWD/radlite_b200/libradlite_b200_$v.so; fi
+  echo "== $v"; env $L python scripts/time_cfg.py 1 3
+done

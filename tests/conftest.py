@@ -31,14 +31,14 @@ def same_bits(a, b):
     batch (tile_kernel below 8 lines, ztile_kernel from 8: they round differently at the 1e-13 level)."""
     import numpy as np
     from radlite_b200 import api
-    if api.DEFAULT_KERNEL in ("z", "tile"):
+    if api.DEFAULT_KERNEL in ("z", "tile", "chan"):
         return np.array_equal(a, b)
     return np.allclose(a, b, rtol=1e-10, atol=0.0)
 
 
-@pytest.fixture(params=["auto", "z", "tile"])
+@pytest.fixture(params=["auto", "z", "tile", "chan"])
 def integrate_kernel(request):
-    """Runs a GPU test once per integrate kernel (library default by regime, ztile_kernel, tile_kernel)."""
+    """Runs a GPU test once per integrate kernel (library default by regime, ztile_kernel, tile_kernel, chan_kernel)."""
     from radlite_b200 import api
     old = api.DEFAULT_KERNEL
     api.DEFAULT_KERNEL = request.param

@@ -301,3 +301,26 @@ def test_opaque_wall_start_is_exact(renderer_cls, oracle_cls, integrate_kernel):
     thin = g.render(1, 8, m.nfr, m.passband, synth.PARSEC, want_image=True)
     assert not np.array_equal(thin["image"], off["image"])
     assert rel_err(thin["flux"], off["flux"]).max() < 1.0
+
+
+def test_chan_and_ztile_kernels_give_the_same_bits(renderer_cls):
+    """chan_kernel (channels of one line across the lanes) and ztile_kernel (lines across the lanes) perform the
+    same operations per (ray, line, channel): image, cube mask and spectrum agree bit for bit."""
+    from radlite_b200 import api
+    old = api.DEFAULT_KERNEL
+    res = {}
+    try:
+        for k in ("z", "chan"):
+            api.DEFAULT_KERNEL = k
+            m = synth.config(2, nr=48, nth=20, nphi=16, nrext=-10, nlines=6)
+            g = renderer_cls(0)
+            g.load_model(m)
+            res[k] = g.render(1, m.nlines, m.nfr, m.passband, synth.PARSEC, want_image=True, want_mask=True)
+            res[k + "_cnt"] = g.counters()
+            g.close()
+    finally:
+        api.DEFAULT_KERNEL = old
+    assert np.array_equal(res["z"]["flux"], res["chan"]["flux"])
+    assert np.array_equal(res["z"]["image"], res["chan"]["image"])
+    assert np.array_equal(res["z"]["cmask"], res["chan"]["cmask"])
+    assert res["z_cnt"] == res["chan_cnt"]
