@@ -2326,12 +2326,27 @@ __global__ void zplan_kernel(RenderParams P) {
         else n++;
       }
     };
+    // a ray whose lines all fit kZCw channels (narrow lines, coarse channels) gets 32 lines per tile, one channel
+    // group: the per-(node, line) part of ztile_kernel is then shared by twice as many channels
+    int gsz0 = P.zlw;
+    if (P.zlw > 1 && P.zlw < 32) {
+      int cmn = 0x7fffffff, cmx = -1;
+      for (int l = 0; l < P.nl; l++) {
+        if (!ni[l]) continue;
+        const int4 r = rg[l];
+        if (r.y < r.x) continue;
+        cmn = min(cmn, r.x);
+        cmx = max(cmx, r.y);
+        if (r.z >= 0) { cmn = min(cmn, r.z); cmx = max(cmx, r.z); }
+      }
+      if (cmx >= cmn && 2 + (cmx - cmn) <= kZCw) gsz0 = 32;
+    }
     int na = 0;
     // pass 0: lines with a channel window; pass 1: lines that need channel 0 only (zcont_kernel's tiles);
     // pass 2: lines without a window whose channel 0 lies inside the ray's velocity span, so that their
     // first skipped channel is integrated as well (telescope.F:557-612; rare)
     for (int pass = 0; pass < 3; pass++) {
-      const int gsz = (pass == 1 || P.zlw > 1 && pass == 2) ? 32 : P.zlw;  // (chan_kernel: one line per tile)
+      const int gsz = pass == 0 ? gsz0 : (pass == 1 || P.zlw > 1) ? 32 : 1;  // (zlw = 1, chan_kernel: one line per tile)
       int gstart = na, cmin = 0x7fffffff, cmax = -1;
       for (int l = 0; l < P.nl; l++) {
         if (!ni[l]) continue;
