@@ -246,8 +246,8 @@ int rl_create(rl_ctx **out, int device) {
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   c->d_status.ensure(1);
-  c->d_counters.ensure(8);
-  cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->st);
+  c->d_counters.ensure(16);
+  cudaMemsetAsync(c->d_counters.p, 0, 16 * sizeof(unsigned long long), c->st);
   cudaStreamSynchronize(c->st);
   *out = c;
   return 0;
@@ -1473,7 +1473,7 @@ int rl_set_wall_tau(rl_ctx *c, double tau) {
 }
 void rl_reset_counters(rl_ctx *c) {
   cudaSetDevice(c->device);
-  cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->st);
+  cudaMemsetAsync(c->d_counters.p, 0, 16 * sizeof(unsigned long long), c->st);
   cudaStreamSynchronize(c->st);
 }
 
@@ -1513,7 +1513,7 @@ long long rl_debug_fetch(rl_ctx *c, const char *what, void *out, long long nbyte
   else if (w == "smin") { src = c->d_smin.p; have = (long long)c->d_smin.n * 8; }
   else if (w == "admin") { src = c->d_admin.p; have = (long long)c->d_admin.n * 8; }
   else if (w == "wstat") { src = c->d_wstat.p; have = 16; }
-  else if (w == "counters") { src = c->d_counters.p; have = 64; }
+  else if (w == "counters") { src = c->d_counters.p; have = 128; }
   else if (w == "node_off") { src = c->d_node_off.p; have = ((long long)c->nray + 1) * 8; }
   else if (w == "rng") { src = c->d_rng.p; have = (long long)c->last_ntask * 16; }
   else if (w == "nitems") { src = c->d_nitems.p; have = (long long)c->last_ntask * 4; }

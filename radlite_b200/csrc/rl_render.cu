@@ -530,6 +530,21 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 constexpr int kSlotBytes = (int)(sizeof(HotNode) + sizeof(ColdNode));
 constexpr int kPairBytes = (int)(sizeof(HotLine) + sizeof(ColdLine));
 
+// The case thresholds of qdr_src_2 in the integrate kernels: dtau > 1e-9 (REAL literal, transfer.F:1542) and
+// dtau > 1e-6 (transfer.F:1517) are tested on the high words of the bit patterns -- one 32-bit integer compare,
+// false for negative values, off the FP64 pipe.  That moves each threshold up by at most 2^-20 of itself (a value
+// in that sliver takes the neighbouring branch, whose result differs by O(dtau^2) of an already negligible term);
+// every integrate kernel uses these same predicates, so a lane's result does not depend on the kernel or on the
+// outcome of a warp vote.  (The reference-ordered scalar path -- centre ray, rectangular imager -- keeps the
+// reference's compares.)
+constexpr int kThinHi = 0x3E112E0B;  // high word of (double)1e-9f = 0x3E112E0BE0000000
+constexpr int kMidHi = 0x3EB0C6F7;   // high word of 1e-6 = 0x3EB0C6F7A0B5ED8D
+__device__ __forceinline__ bool gt_thin(double d) { return __double2hiint(d) > kThinHi; }
+__device__ __forceinline__ bool gt_mid(double d) { return __double2hiint(d) > kMidHi; }
+// min of two non-NaN-or-rescued values: a NaN in a (0/0 of a degenerate step) selects b like fmin does, without
+// fmin's NaN-quieting instruction sequence
+__device__ __forceinline__ double min_sel(double a, double b) { return a < b ? a : b; }
+
 // n/x: hardware reciprocal seed (MUFU.RCP64H, about 2^-9) and two Newton steps, the second fused
 // with the multiplication: relative error ~ seed^4 < 2e-11
 __device__ __forceinline__ double div_fast(double n, double x) {
@@ -584,7 +599,7 @@ __device__ __forceinline__ void step_coeffs(double alp0, double r0, double src1,
   const double ee1 = dtau - e0;
   const double bt = div_fast(ee1, dtau);
   const double hb = 0.5 * dtau;
-  const bool thick = dtau > 1.e-6;
+  const bool thick = gt_mid(dtau);
   const double b = thick ? bt : hb;
   const double a = thick ? (e0 - bt) : hb;
   x = thick ? xpe : (1.0 - dtau);
@@ -592,7 +607,7 @@ __device__ __forceinline__ void step_coeffs(double alp0, double r0, double src1,
   const double s_a = p0 ? r0 : (p1 ? r1 : 0.0);
   const double s_b = p1 ? r1 : (p0 ? r0 : 0.0);
   qv = fma(a, s_a, b * s_b);
-  qv = (dtau > (double)1e-9f) ? fmin(qv, theomax) : theomax;
+  qv = gt_thin(dtau) ? min_sel(qv, theomax) : theomax;
 }
 
 __device__ __forceinline__ void full_step(double &inten, double alp0, double r0, double src1, double alp1,
@@ -614,7 +629,7 @@ __device__ __forceinline__ void step_onediv(double alp0, double src0, double alp
                                             double theomax, uint32_t T1, double &x, double &qv) {
   const double xpe = expneg_tab(dtau, T1, 0);
   const double e0 = 1.0 - xpe, e1 = dtau - e0;
-  const bool thick = dtau > 1.e-6;
+  const bool thick = gt_mid(dtau);
   const bool p0 = alp0 > kAlpMin, p1 = alp1 > kAlpMin;
   const double nA = p0 ? src0 : (p1 ? src1 : 0.0), dA = p0 ? alp0 : (p1 ? alp1 : 1.0);
   const double nB = p1 ? src1 : (p0 ? src0 : 0.0), dB = p1 ? alp1 : (p0 ? alp0 : 1.0);
@@ -624,7 +639,7 @@ __device__ __forceinline__ void step_onediv(double alp0, double src0, double alp
   const double num = fma(ca, nA * dB, cb * (nB * dA));
   x = thick ? xpe : (1.0 - dtau);
   qv = div_fast(num, den);
-  qv = (dtau > (double)1e-9f) ? fmin(qv, theomax) : theomax;
+  qv = gt_thin(dtau) ? min_sel(qv, theomax) : theomax;
 }
 
 __shared__ double s_T1[kTabN];       // 2^(j/kTabN): the exp table every integrate kernel fills at block start
@@ -1031,7 +1046,7 @@ __device__ __forceinline__ void jam_steps(uint32_t an, uint32_t ah, uint32_t str
     const double a0 = k ? alp1[k - 1] : it.alp0, s0 = k ? src1[k - 1] : it.src0;
     dtau[k] = hds[k] * (a0 + alp1[k]);
     theo[k] = hds[k] * (s0 + src1[k]);
-    work = work || (dtau[k] > (double)1e-9f);
+    work = work || gt_thin(dtau[k]);
     anyk1 |= k1hi[k];
   }
   work = work || (anyk1 < 0);  // inverted populations force the full path, which carries the maser test
@@ -1431,10 +1446,22 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
   const int cwS = cw3 | 1;  // table columns per channel group (odd: the groups' reads never conflict)
   const int NB = min(31 - RL_ZPD, kZTab / (GW * cwS) - 1);  // nodes per batch
   const uint32_t rowB = (uint32_t)(GW * cwS) * 8u;  // bytes of one node's row of the profile table
-  const uint32_t Mdiv = ((1u << 20) + (uint32_t)cw3 - 1u) / (uint32_t)cw3;
+  const int W = GW * cw3;                                // columns of the profile table
+  const int fsi = 32 / W, fqi = 32 - fsi * W;            // the fill loop's step of 32 entries in (row, column)
+  const int fs0 = lane / W, fq0 = lane - fs0 * W;        // this lane's first entry
   unsigned mbits = 0, xtra = 0;
-  constexpr long long kThin = 0x3E112E0BE0000000LL;  // bit pattern of (double)1e-9f (transfer.F:1542, REAL literal)
-  constexpr long long kMid = 0x3EB0C6F7A0B5ED8DLL;   // bit pattern of 1e-6 (transfer.F:1517)
+#ifdef RL_STATS
+  unsigned long long st[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  auto st_far = [&](int base, uint32_t ep_a, uint32_t ec_a) {
+    for (int c = 0; c < cw; c++) {
+      const double em = fmax(lds_f64(ep_a + 8u * (uint32_t)c), lds_f64(ec_a + 8u * (uint32_t)c));
+      st[base]++;
+      if (em == 0.0) st[base + 1]++;
+      if (em <= 3.72e-44) st[base + 2]++;
+      if (em <= 1.6e-28) st[base + 3]++;
+    }
+  };
+#endif
 
   // the two (four for extra points) stencil cells of a node; the first pair is pulled into L1 one node
   // ahead (no registers held across the channel loop)
@@ -1516,16 +1543,26 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
         if (c0 - 1 + k < N) prefetch(snx[k].offA, snx[k].offB);
     }
 #endif
-    {  // profile table of the batch: rows = nodes c0-1 .. c0+cnt-1, columns = (channel group, slot)
-      const int tot = (cnt + 1) * GW * cw3;
-      for (int idx = lane; idx < tot; idx += 32) {
-        const int tq = (int)(((uint32_t)idx * Mdiv) >> 20);  // idx / cw3 (exact: idx < 2^10)
-        const int c = idx - tq * cw3, gg = tq & (GW - 1), s = tq >> gws;
-        const int j = min(j0 + gg + c * GW, jmax);
+    {  // profile table of the batch: rows = nodes c0-1 .. c0+cnt-1, columns = (channel group, slot).  The lanes
+       // walk (row s, column q) with q = slot * GW + group -- the position in the tile's channel list is then
+       // j0 + q, group and slot fall out of q by mask and shift -- advancing (s, q) by 32 entries per iteration
+       // without a division
+      int q = fq0, sr = fs0;
+      const int rows = cnt + 1;
+      while (sr < rows) {
+        const int gg = q & (GW - 1), c = q >> gws;
+        const int j = min(j0 + q, jmax);
         const double vel = __ldg(P.velz + (j ? cmin + j - 1 : 0));
-        const double e = gauss_tab(fma(vel, snx[s].ian, -snx[s].dvi), T1, 0);
-        asm volatile("st.shared.f64 [%0], %1;" ::"r"(et0 + (uint32_t)(((s << gws) + gg) * cwS + c) * 8u), "d"(e)
+        const double2 sc = *reinterpret_cast<const double2 *>(&snx[sr].ian);  // {ian, dvi}
+        const double e = gauss_tab(fma(vel, sc.x, -sc.y), T1, 0);
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(et0 + (uint32_t)(((sr << gws) + gg) * cwS + c) * 8u), "d"(e)
                      : "memory");
+        q += fqi;
+        sr += fsi;
+        if (q >= W) {
+          q -= W;
+          sr++;
+        }
       }
     }
     __syncwarp();
@@ -1548,8 +1585,11 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
         // the profile is <= 1: if D + |P| + |Q| <= 1e-9 on every lane, every channel of the node takes the
         // thin branch of transfer.F:1522-1524,1545 (Q = theomax, xp = 1 - dtau): no votes, no branches, all
         // channels' chains independent
-        const bool maybe = neg | (__double_as_longlong(D + fabs(Pq) + fabs(Q)) > kThin);
+        const bool maybe = neg | gt_thin(D + fabs(Pq) + fabs(Q));
         if (cw3 == CW && !__any_sync(0xffffffffu, maybe)) {
+#ifdef RL_STATS
+          st_far(0, ep_a, ec_a);
+#endif
 #pragma unroll
           for (int c = 0; c < CW; c++) {
             const double ep = lds_f64(ep_a + 8u * (uint32_t)c), ec = lds_f64(ec_a + 8u * (uint32_t)c);
@@ -1559,42 +1599,39 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
         } else
 #endif
         {
+#ifdef RL_STATS
+          st_far(4, ep_a, ec_a);
+#endif
 #pragma unroll
           for (int cb = 0; cb < CW; cb += 3) {
             if (cb < cw) {
               double ep[3], ec[3], dtau[3], theo[3];
-              bool work = neg, thin_some = false;
 #pragma unroll
               for (int k = 0; k < 3; k++) {
                 ep[k] = lds_f64(ep_a + 8u * (uint32_t)(cb + k));
                 ec[k] = lds_f64(ec_a + 8u * (uint32_t)(cb + k));
                 dtau[k] = fma(Pq, ep[k], fma(Q, ec[k], D));
                 theo[k] = fma(R, ep[k], fma(S, ec[k], Th));
-                // dtau > 1e-9 (REAL literal, transfer.F:1542) as an integer compare of the bit patterns:
-                // same order for positive values, false for negative ones; keeps the FP64 pipe for the
-                // arithmetic
-                work = work | (__double_as_longlong(dtau[k]) > kThin);
-                thin_some = thin_some | !(__double_as_longlong(dtau[k]) > kMid);
               }
+              // gt_thin / gt_mid of the three channels at once: largest and smallest high word
+              const int h0 = __double2hiint(dtau[0]), h1 = __double2hiint(dtau[1]), h2 = __double2hiint(dtau[2]);
+              const bool work = neg | (max(max(h0, h1), h2) > kThinHi);
+              const bool thin_some = !(min(min(h0, h1), h2) > kMidHi);
               if (!__any_sync(0xffffffffu, work)) {
+#ifdef RL_STATS
+                st[8]++;
+#endif
                 // transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau
 #pragma unroll
                 for (int k = 0; k < 3; k++) I[cb + k] = fma(I[cb + k], 1.0 - dtau[k], theo[k]);
               } else {
-#ifdef RL_STATS
-                {
-                  const double em = fmax(fmax(fmax(ep[0], ec[0]), fmax(ep[1], ec[1])), fmax(ep[2], ec[2]));
-                  const bool far = !__any_sync(0xffffffffu, em > 8.0e-28);
-                  if (lane == 0) {
-                    atomicAdd(&P.counters[4], 1ull);
-                    if (far) atomicAdd(&P.counters[5], 1ull);
-                  }
-                }
-#endif
                 const double K0 = v0.kk * nrm0, A0 = v0.cN * nrm0, K1 = v1.kk * nrm1, A1 = v1.cN * nrm1;
 #if RL_ZSTREAM
                 // lanes whose dust opacity alone is positive never see alpha <= 0 unless the line inverts
                 const bool odd = neg | thin_some | !(v0.ad > kAlpMin) | !(v1.ad > kAlpMin) | (v0.kk < 0.0);
+#ifdef RL_STATS
+                st[__any_sync(0xffffffffu, odd) ? 10 : 9]++;
+#endif
                 if (!__any_sync(0xffffffffu, odd)) {
                   // every lane: dtau > 1e-6 and both opacities positive -- qdr_src_2 without its case
                   // selections (the operations of step_coeffs on this branch, bit for bit)
@@ -1609,12 +1646,12 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
                     const double e0 = 1.0 - xpe, e1 = dtau[k] - e0;
                     const double den = dtau[k] * (alp0 * alp1);
                     const double num = fma(fma(e0, dtau[k], -e1), src0 * alp1, e1 * (src1 * alp0));
-                    const double qv = fmin(div_fast(num, den), theo[k]);
+                    const double qv = min_sel(div_fast(num, den), theo[k]);
 #else
                     const double r0 = div_fast(src0, alp0), r1 = div_fast(src1, alp1);
                     const double e0 = 1.0 - xpe;
                     const double bt = div_fast(dtau[k] - e0, dtau[k]);
-                    const double qv = fmin(fma(e0 - bt, r0, bt * r1), theo[k]);
+                    const double qv = min_sel(fma(e0 - bt, r0, bt * r1), theo[k]);
 #endif
                     I[cb + k] = fma(I[cb + k], xpe, qv);
                   }
@@ -1642,6 +1679,9 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
           }
         }
       } else {
+#ifdef RL_STATS
+        st[11]++;
+#endif
         double tmp[CW];
 #pragma unroll
         for (int c = 0; c < CW; c++) tmp[c] = I[c];
@@ -1680,6 +1720,10 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
       r++;
     }
   }
+#ifdef RL_STATS
+  if ((lane & ((1 << lws) - 1)) == 0)  // one lane per channel group
+    for (int k = 0; k < 12; k++) atomicAdd(&P.counters[4 + k], st[k]);
+#endif
   if (mbits & realbits) atomicOr(&P.maser[l], 1);
   // work counters: every item walks the ray's N-1 segments (the reference's count, whether or not an opaque
   // wall shortened the walk here); sub-gridding adds extra elements; executed = what this kernel integrated
@@ -1754,7 +1798,6 @@ __global__ void __launch_bounds__(32 * kZcWarps, RL_ZCMINB) zcont_kernel(const _
   const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
   ZCNode *sn = s_zc[warp];
   const double vel0 = __ldg(P.velz);
-  constexpr long long kThin = 0x3E112E0BE0000000LL;  // bit pattern of (double)1e-9f (transfer.F:1542, REAL literal)
   unsigned mbits = 0, xtra = 0;
 
   // interpolated cell values of this lane's line at a staged node: all four fields, or the dust pair only
@@ -1794,7 +1837,7 @@ __global__ void __launch_bounds__(32 * kZcWarps, RL_ZCMINB) zcont_kernel(const _
     const double Pq = hn0 * v0.kk, Q = hn1 * v1.kk, R = hn0 * v0.cN, S = hn1 * v1.cN;
     const bool neg = v1.kk < 0.0;
     const double dtau = fma(Pq, ep, fma(Q, ec, D)), theo = fma(R, ep, fma(S, ec, Th));
-    const bool work = neg | (__double_as_longlong(dtau) > kThin);
+    const bool work = neg | gt_thin(dtau);
     if (!__any_sync(0xffffffffu, work)) {
       I = fma(I, 1.0 - dtau, theo);
     } else {
@@ -1874,7 +1917,7 @@ __global__ void __launch_bounds__(32 * kZcWarps, RL_ZCMINB) zcont_kernel(const _
         const double h1 = x1->hds, h2 = x2->hds;
         const double D1 = h1 * (v0.ad + d1.y), T1h = h1 * (v0.sd + d1.x);
         const double D2 = h2 * (d1.y + d2.y), T2h = h2 * (d1.x + d2.x);
-        const bool work = (__double_as_longlong(D1) > kThin) | (__double_as_longlong(D2) > kThin);
+        const bool work = gt_thin(D1) | gt_thin(D2);
         if (!__any_sync(0xffffffffu, work)) {
           I = fma(fma(I, 1.0 - D1, T1h), 1.0 - D2, T2h);
         } else {
@@ -2102,7 +2145,6 @@ __global__ void __launch_bounds__(32, RL_CMINB) chan_kernel(const __grid_constan
     for (int c = 0; c < CW; c++) I[c] = 0.0;
   }
   unsigned mbits = 0, xtra = 0;
-  constexpr long long kThin = 0x3E112E0BE0000000LL;  // bit pattern of (double)1e-9f (transfer.F:1542, REAL literal)
 
   for (int c0 = ns; c0 < N; c0 += 31) {
     const int cnt = min(31, N - c0);
@@ -2164,7 +2206,7 @@ __global__ void __launch_bounds__(32, RL_CMINB) chan_kernel(const __grid_constan
         step_onediv(v0.ad, v0.sd, v.ad, v.sd, g.D, g.Th, T1, g.xd, g.qd);
         g.fl = fl;
         g.neg = v.kk < 0.0 ? 1u : 0u;  // inverted populations: full path, which carries the maser test
-        g.thin = (!g.neg && !(__double_as_longlong(g.D + fabs(g.Pq) + fabs(g.Q)) > kThin)) ? 1u : 0u;
+        g.thin = (!g.neg && !gt_thin(g.D + fabs(g.Pq) + fabs(g.Q))) ? 1u : 0u;
         // every opacity of the segment is positive whatever the profile (it is >= 0): dust opacity positive
         // at both nodes, no inversion at either
         g.upos = (!g.neg && v0.ad > kAlpMin && v.ad > kAlpMin && !(v0.kk * nrm0 < 0.0)) ? 1u : 0u;
@@ -2193,7 +2235,7 @@ __global__ void __launch_bounds__(32, RL_CMINB) chan_kernel(const __grid_constan
               const double ec = gauss_tab(u, T1, 0);
               const double dtau = fma(g->Pq, ep[c], fma(g->Q, ec, g->D));
               const double theo = fma(g->R, ep[c], fma(g->S, ec, g->Th));
-              if (g->thin || !__any_sync(0xffffffffu, __double_as_longlong(dtau) > kThin)) {
+              if (g->thin || !__any_sync(0xffffffffu, gt_thin(dtau))) {
                 // transfer.F:1522-1524,1545: Q = theomax, xp = 1 - dtau
                 I[c] = fma(I[c], 1.0 - dtau, theo);
               } else {
@@ -2205,14 +2247,14 @@ __global__ void __launch_bounds__(32, RL_CMINB) chan_kernel(const __grid_constan
                   // step_onediv with both opacities known to be positive
                   const double xpe = expneg_tab(dtau, T1, 0);
                   const double e0 = 1.0 - xpe, e1 = dtau - e0;
-                  const bool thick = dtau > 1.e-6;
+                  const bool thick = gt_mid(dtau);
                   const double hb = 0.5 * dtau;
                   const double ca = thick ? fma(e0, dtau, -e1) : hb, cb = thick ? e1 : hb, dd = thick ? dtau : 1.0;
                   const double den = dd * (alp0 * alp1);
                   const double num = fma(ca, src0 * alp1, cb * (src1 * alp0));
                   x = thick ? xpe : (1.0 - dtau);
                   q = div_fast(num, den);
-                  q = (dtau > (double)1e-9f) ? fmin(q, theo) : theo;
+                  q = gt_thin(dtau) ? min_sel(q, theo) : theo;
                 } else {
                   step_onediv(alp0, src0, alp1, src1, dtau, theo, T1, x, q);
                   if (g->neg && (n1p->K1 * ec) * n1p->ds < (double)(-0.01f)) mbits |= 1u << c;  // telescope.F:4295
