@@ -326,20 +326,32 @@ def run_gpu(args):
             return t
 
         # warm-up, with the blocks re-cut from the measured device time per rank: the plan's work estimate is a
-        # model; what a rank really needs per unit of estimated work corrects it (two or three rounds settle it)
-        cost_np = cost.cpu().numpy().copy()
-        for w in range(args.warmup):
-            t = step_strong()
+        # model; what a rank really needs per unit of estimated work corrects it (shard.rebalance_rings).  The
+        # first step only allocates; then at least args.warmup steps, each followed by a correction while the
+        # slowest rank is more than 2 % above the mean, at most 10; the cut with the smallest slowest-rank time
+        # seen is the one that is timed (one more untimed step with it follows).
+        def rank_times(t):
             tk = torch.tensor([t[4]], dtype=torch.float64, device=dev)
             allt = [torch.zeros_like(tk) for _ in range(world)]
             dist.all_gather(allt, tk)
-            allt = np.array([float(x.item()) for x in allt])
-            if w < args.warmup - 1 and allt.min() > 0:
-                for k, (a, b) in enumerate(blocks):
-                    if b >= a:
-                        cost_np[a:b + 1] *= allt[k] / max(cost_np[a:b + 1].sum(), 1e-300)
-                blocks = shard.split_rings(nrr, world, cost_np)
-                lo, hi = blocks[rank]
+            return np.array([float(x.item()) for x in allt])
+
+        cost_np = cost.cpu().numpy().copy()
+        step_strong()
+        best = None
+        recuts = 0
+        for w in range(max(args.warmup, 10)):
+            allt = rank_times(step_strong())
+            if best is None or allt.max() < best[0]:
+                best = (allt.max(), list(blocks))
+            if allt.min() <= 0 or (w >= args.warmup - 1 and allt.max() <= 1.02 * allt.mean()):
+                break
+            cost_np, blocks = shard.rebalance_rings(cost_np, blocks, allt)
+            lo, hi = blocks[rank]
+            recuts += 1
+        blocks = best[1]
+        lo, hi = blocks[rank]
+        step_strong()
         g.reset_counters()
         l0 = g.launch_count()
         sampler = ClockSampler(local, args.clock_ms) if rank == 0 else None

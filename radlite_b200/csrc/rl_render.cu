@@ -165,8 +165,11 @@ __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) {
 }
 
 __global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
-  __shared__ double s_dv[kSpanThreads];
-  __shared__ uint32_t s_on[4][kSpanThreads], s_un[4][kSpanThreads];
+  // Omega.v/c of the parked nodes as REAL*4: minvel / maxvel are REAL*4 in the reference (common_telescope.h:17)
+  // and rounding to float is monotonic, so the float of the minimum is the minimum of the floats -- and
+  // single-precision min / max are one instruction each where the double ones are compare-and-select sequences
+  __shared__ float s_dv[kSpanThreads];
+  __shared__ uint32_t s_on[4][kSpanThreads];
   const int ray = blockIdx.x, tid = threadIdx.x;
   const int l = tid;  // the line this thread owns in the second phase
   const long long task = (long long)ray * P.nl + l;
@@ -189,10 +192,9 @@ __global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
     return;
   }
   const long long n0 = P.node_off[ray], n1 = P.node_off[ray + 1];
-  const double4 *cellL = P.cellL + l;
   const int w = (l >> 5) & 3;
   const uint32_t bit = 1u << (l & 31);
-  double vmin = 2.0, vmax = -2.0;
+  float vmin = 1.0f, vmax = -1.0f;  // initial values of telescope.F:388-391
   // telescope.F:4265-4270: start node of every segment, i.e. all nodes but the last
   for (long long c = n0; c < n1 - 1; c += kSpanThreads) {
     const int cnt = (int)min((long long)kSpanThreads, n1 - 1 - c);
@@ -213,27 +215,33 @@ __global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
         on = and4(on, __ldg(&mk[nd.cells.w].on));
         off = and4(off, __ldg(&mk[nd.cells.w].off));
       }
-      s_dv[tid] = nd.dvmu;
-      s_on[0][tid] = on.x; s_on[1][tid] = on.y; s_on[2][tid] = on.z; s_on[3][tid] = on.w;
-      s_un[0][tid] = ~(on.x | off.x); s_un[1][tid] = ~(on.y | off.y);
-      s_un[2][tid] = ~(on.z | off.z); s_un[3][tid] = ~(on.w | off.w);
+      // lines whose stencil cells disagree (or sit on the threshold): the interpolation decides.  Resolved here,
+      // by the thread that owns the node -- the 128 nodes of the chunk in parallel -- so that the walk over the
+      // parked nodes below touches shared memory only
+      uint32_t o4[4] = {on.x, on.y, on.z, on.w};
+      const uint32_t f4[4] = {off.x, off.y, off.z, off.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int nk = min(32, max(0, P.nl - 32 * k));  // lines of this word
+        uint32_t un = ~(o4[k] | f4[k]) & (nk >= 32 ? 0xffffffffu : ((1u << nk) - 1u));
+        while (un) {
+          const int b = __ffs((int)un) - 1;
+          un &= un - 1u;
+          const double4 v = gather_line(P.cellL + (32 * k + b), (size_t)P.nl, nd.cells, nd.wr, nd.wt, icr);
+          if (v.z + v.w > P.levthres) o4[k] |= 1u << b;
+        }
+        s_on[k][tid] = o4[k];
+      }
+      s_dv[tid] = (float)nd.dvmu;
     }
     __syncthreads();
     if (l < P.nl) {
+#pragma unroll 4
       for (int t = 0; t < cnt; t++) {
-        const uint32_t o = s_on[w][t], u = s_un[w][t];
-        if ((o | u) & bit) {
-          bool in = (o & bit) != 0;
-          if (!in) {  // stencil cells disagree (or sit on the threshold): evaluate the interpolation
-            const Node nd = load_node(P.nodes.rec, c + t);
-            const double4 v = gather_line(cellL, (size_t)P.nl, nd.cells, nd.wr, nd.wt, nd.flags & kFlagIcrMask);
-            in = v.z + v.w > P.levthres;
-          }
-          if (in) {
-            const double dv = s_dv[t];
-            vmin = fmin(vmin, dv);
-            vmax = fmax(vmax, dv);
-          }
+        if (s_on[w][t] & bit) {
+          const float dv = s_dv[t];
+          vmin = fminf(vmin, dv);
+          vmax = fmaxf(vmax, dv);
         }
       }
     }
@@ -241,8 +249,7 @@ __global__ void __launch_bounds__(kSpanThreads) span_kernel(RenderParams P) {
   }
   if (l >= P.nl) return;
   // REAL*4 minvel/maxvel (common_telescope.h:17), initial values 1 and -1 (telescope.F:388-391)
-  const float minvel = (vmin < 1.0) ? (float)vmin : 1.0f;
-  const float maxvel = (vmax > -1.0) ? (float)vmax : -1.0f;
+  const float minvel = vmin, maxvel = vmax;
   const double hi_lim = (double)maxvel + 2.f * P.aksmax_c;
   const double lo_lim = (double)minvel - 2.f * P.aksmax_c;
   const double *velo = P.velo + (size_t)l * P.nfr;
@@ -520,6 +527,11 @@ __device__ __forceinline__ T *smem_ptr(uint32_t a) {
 __device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
   return v;
 }
 __device__ __forceinline__ double lds_f64(uint32_t a) {
@@ -1388,9 +1400,14 @@ __global__ void __maxnreg__(RL_ZMAXREG) ztile_kernel
 __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_kernel
 #endif
 (const __grid_constant__ RenderParams P) {
-  __shared__ double s_et[kZWarps][kZTab];
-  __shared__ NodeRec s_nd[kZWarps][32];
-  __shared__ ZNx s_nx[kZWarps][32];
+  // per warp: profile table, staged node records, derived records -- one struct, so that the hot loop addresses
+  // all three as (one 32-bit shared-window base) + constant
+  struct __align__(16) ZShm {
+    double et[kZTab];
+    NodeRec nd[32];
+    ZNx nx[32];
+  };
+  __shared__ ZShm s_z[kZWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < kTabN) s_T1[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kTabN));
   __syncthreads();
@@ -1429,9 +1446,11 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
     I[c] = (P.out_itype == 3) ? __ldg(&P.isrf_line[(size_t)l * P.nfr + chan_of(c)]) : __ldg(&Lp->i_outer);
 
   const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
-  const uint32_t et0 = (uint32_t)__cvta_generic_to_shared(&s_et[warp][0]);
-  NodeRec *snd = s_nd[warp];
-  ZNx *snx = s_nx[warp];
+  const uint32_t et0 = (uint32_t)__cvta_generic_to_shared(&s_z[warp].et[0]);
+  constexpr uint32_t kNdOff = (uint32_t)(kZTab * sizeof(double)), kNxOff = kNdOff + 32u * (uint32_t)sizeof(NodeRec);
+  static_assert(sizeof(ZNx) == 48 && sizeof(NodeRec) == 64, "record sizes the hot loop's offsets assume");
+  NodeRec *snd = s_z[warp].nd;
+  ZNx *snx = s_z[warp].nx;
   const long long n0 = P.node_off[ray];
   const int N = (int)(P.node_off[ray + 1] - n0);
   const NodeRec *__restrict__ rec = P.nodes.rec + n0;
@@ -1567,12 +1586,29 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
     }
     __syncwarp();
     for (int s = 1; s <= cnt; s++) {
-      const NodeRec *nd = snd + s;
-      const ZNx nx = snx[s];
+      const NodeRec *nd = snd + s;  // (generic pointer: the rare paths only)
+      const uint32_t nxa = et0 + kNxOff + 48u * (uint32_t)s, nda = et0 + kNdOff + 64u * (uint32_t)s;
+      ZNx nx;
+      {
+        const uint2 fi = lds_u32x2(nxa + 8u);
+        const double2 wh = lds_f64x2(nxa + 16u);
+        nx.fl = fi.x;
+        nx.icr = fi.y;
+        nx.w = wh.x;
+        nx.hds = wh.y;
+#if !RL_ZPIPE
+        const uint2 ob = lds_u32x2(nxa);
+        nx.offA = ob.x;
+        nx.offB = ob.y;
+#endif
+      }
       const uint32_t fl = nx.fl;
       const ZVal v1 = zvals(gather(nx, nd), c_src, cb_du, cb_ud);
-      if (c0 - 1 + s + RL_ZPD < N) prefetch(snx[s + RL_ZPD].offA, snx[s + RL_ZPD].offB);
-      const double nrm1 = knorm * nd->inv_lwav;
+      if (c0 - 1 + s + RL_ZPD < N) {
+        const uint2 ob = lds_u32x2(nxa + 48u * RL_ZPD);
+        prefetch(ob.x, ob.y);
+      }
+      const double nrm1 = knorm * lds_f64(nda + 24u);  // NodeRec::inv_lwav
       const uint32_t ep_a = et0 + (uint32_t)(((s - 1) << gws) + g) * (uint32_t)(cwS * 8);
       const uint32_t ec_a = ep_a + rowB;
       if (fl == 0) {
@@ -1690,7 +1726,7 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
         sg.lwav = 0.5 * (snd[s - 1].lw + nd->lw);
         sg.dv0 = snd[s - 1].dvmu;
         sg.dv1 = nd->dvmu;
-        sg.ian = nx.ian;
+        sg.ian = snx[s].ian;
         sg.nrm0 = nrm0;
         sg.nrm1 = nrm1;
         sg.v0 = v0;
@@ -2924,13 +2960,32 @@ __global__ void __launch_bounds__(128) ringsum_kernel(RenderParams P, const doub
     for (int ip = 0; ip < P.nphi; ip++) dslum = dslum + I[(size_t)ip * P.nfr];
   } else {
     // skipped channels carry the row's continuum (telescope.F:582-612), never written in this mode
-    long long task = ((long long)(1 + (ir - 1) * P.nphi)) * P.nl + l;
-    for (int ip = 0; ip < P.nphi; ip++, task += P.nl) {
-      const int4 rg = __ldg(&P.rng[task]);
-      const double *row = I - c + (size_t)ip * P.nfr;
-      const bool own = (c == 0) || (c >= rg.x && c <= rg.y) || (c == rg.z) || P.dense[task];
-      const int src = own ? c : ((rg.w == 0) ? 0 : rg.z);
-      dslum = dslum + row[src];
+    // (the additions stay in phi order; the loads of kU pixels -- channel range, then the intensity it selects --
+    // are in flight together: the loop is bound by their latency, not by their number)
+    constexpr int kU = 6;
+    const long long task0 = ((long long)(1 + (ir - 1) * P.nphi)) * P.nl + l;
+    for (int ip0 = 0; ip0 < P.nphi; ip0 += kU) {
+      int4 rg[kU];
+      unsigned char dn[kU];
+      double v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int ip = min(ip0 + u, P.nphi - 1);
+        const long long task = task0 + (long long)ip * P.nl;
+        rg[u] = __ldg(&P.rng[task]);
+        dn[u] = P.dense[task];
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int ip = min(ip0 + u, P.nphi - 1);
+        const double *row = I - c + (size_t)ip * P.nfr;
+        const bool own = (c == 0) || (c >= rg[u].x && c <= rg[u].y) || (c == rg[u].z) || dn[u];
+        const int src = own ? c : ((rg[u].w == 0) ? 0 : rg[u].z);
+        v[u] = row[src];
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++)
+        if (ip0 + u < P.nphi) dslum = dslum + v[u];
     }
   }
   dslum = dslum / (1.0 * P.nphi);

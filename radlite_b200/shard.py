@@ -54,6 +54,21 @@ def split_rings(nrr: int, world: int, cost=None):
     return [(edges[k], edges[k + 1] - 1) for k in range(world)]
 
 
+def rebalance_rings(cost, blocks, times):
+    """One correction of the per-ring work estimate from measured times: the estimate of every ring of block k
+    is scaled so that the block's sum equals the time rank k needed (``times[k]``, any unit), and the rings are
+    cut again.  A rank's time also holds a part that does not move with its rings (launches, per-line tables),
+    which this model spreads over the block's rings, so a step under-corrects a little and the iteration
+    approaches equal times from one side; three or four steps settle it.  Returns (cost, blocks)."""
+    cost = np.array(cost, dtype=np.float64)
+    times = np.asarray(times, dtype=np.float64)
+    world = len(blocks)
+    for k, (a, b) in enumerate(blocks):
+        if b >= a and times[k] > 0:
+            cost[a:b + 1] *= times[k] / max(cost[a:b + 1].sum(), 1e-300)
+    return cost, split_rings(len(cost) - 1, world, cost)
+
+
 def _dist():
     import torch.distributed as dist
     return dist

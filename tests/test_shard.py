@@ -120,3 +120,27 @@ def test_single_rank_paths_equal_unsharded(oracle_cls):
     o.load_model(m)
     ref = o.render(1, m.nlines, m.nfr, m.passband, synth.PARSEC)["flux"]
     assert np.array_equal(a, ref) and np.array_equal(b, ref)
+
+
+def test_rebalance_rings_converges_with_a_fixed_part():
+    """Ranks whose time is a fixed part plus the (unknown) true cost of their rings: a few corrections of a
+    wrong estimate bring the slowest rank within a few per cent of the mean."""
+    rng = np.random.default_rng(5)
+    nrr, world, fixed = 269, 8, 2.4
+    ir = np.arange(nrr + 1)
+    true = 0.02 + 0.3 * np.exp(-((ir - 70) / 60.0) ** 2) + 0.1 * (ir > 200)
+    true *= 36.0 / true.sum()
+    est = np.ones(nrr + 1)  # a poor first estimate
+    blocks = shard.split_rings(nrr, world, est)
+
+    def measure(blocks):
+        return np.array([fixed + true[a:b + 1].sum() for a, b in blocks]) * (1 + 0.005 * rng.standard_normal(world))
+
+    t0 = measure(blocks)
+    for _ in range(5):
+        est, blocks = shard.rebalance_rings(est, blocks, measure(blocks))
+        assert blocks[0][0] == 0 and blocks[-1][1] == nrr
+        assert all(blocks[k + 1][0] == blocks[k][1] + 1 for k in range(world - 1))
+    t = measure(blocks)
+    assert t.max() < 0.75 * t0.max()
+    assert t.max() / t.mean() < 1.06, (t, blocks)
