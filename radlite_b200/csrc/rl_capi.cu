@@ -7,6 +7,7 @@
 #include "../../include/radlite_b200.h"
 #include "rl_types.h"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
@@ -166,7 +167,8 @@ struct rl_ctx {
   DevBuf<int4> d_rng;
   DevBuf<CellMask> d_masks;
   DevBuf<TileDesc> d_tiles;
-  DevBuf<ZTile> d_ztiles;
+  DevBuf<ZTile> d_ztiles, d_ztiles_in;
+  DevBuf<unsigned> d_zkeys, d_zkeys_out;
   DevBuf<double> d_admin, d_smin;   // [ncell] smallest dust opacity / source function of the batch's lines (opaque-wall start)
   DevBuf<unsigned long long> d_wstat;  // {largest source function (bit pattern), inverted flag}
   DevBuf<int> d_nstart;
@@ -1056,6 +1058,8 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
       P.zlw = z;
     }
     P.ztiles = nullptr;
+    P.ztiles_in = nullptr;
+    P.zkeys = nullptr;
     P.nztile = 0;
     P.nstart = nullptr;
     P.wall_tau = c->wall_tau;
@@ -1114,11 +1118,36 @@ static int render_impl(rl_ctx *c, int iline0, int nl, int nfr, double vmax_kms, 
     P.tiles = c->d_tiles.p;
     CU(c->d_ztiles.ensure(std::max<size_t>(1, P.use_z ? n_all : 1)));
     P.ztiles = c->d_ztiles.p;
+    P.ztiles_in = nullptr;
+    P.zkeys = nullptr;
+    // ztile_kernel's tiles longest first (a block is one warp walking one ray: the last blocks of the launch
+    // decide how long its tail is -- a tenth of the integrate phase of an eighth of the rays, multi-GPU)
+#ifdef RL_NO_COST_ORDER
+    const bool cost_order = false;
+#else
+    const bool cost_order = P.use_z && P.zlw > 1 && n_main > 1;
+#endif
+    if (cost_order) {
+      CU(c->d_ztiles_in.ensure(n_main));
+      CU(c->d_zkeys.ensure(n_main));
+      CU(c->d_zkeys_out.ensure(n_main));
+      P.ztiles_in = c->d_ztiles_in.p;
+      P.zkeys = c->d_zkeys.p;
+    }
     P.nztile = n_main;
     c->last_nztile = P.use_z ? n_all : 0;
     c->last_ntask = (long long)ntask;
     if (n_all) {
       launch_plan(P, true, c->st);
+      c->launches++;
+    }
+    if (cost_order) {
+      size_t tmp_bytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->d_zkeys.p, c->d_zkeys_out.p, c->d_ztiles_in.p,
+                                      c->d_ztiles.p, (int)n_main, 0, 12, c->st);
+      CU(c->d_scan_tmp.ensure(tmp_bytes));
+      CU(cub::DeviceRadixSort::SortPairs(c->d_scan_tmp.p, tmp_bytes, c->d_zkeys.p, c->d_zkeys_out.p,
+                                         c->d_ztiles_in.p, c->d_ztiles.p, (int)n_main, 0, 12, c->st));
       c->launches++;
     }
     if (ring_cost) {  // plan only: work estimate per camera ring (rl_plan_costs), accumulated over the batches

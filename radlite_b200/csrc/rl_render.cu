@@ -1372,6 +1372,28 @@ __device__ __noinline__ unsigned zflagged(double *Ic, const ZSeg &g, uint32_t fl
   return mb;
 }
 
+// Three channels of one unflagged segment through the fully general step (an opacity that is not positive
+// somewhere in the warp: dust-free cells, inverted populations), out of line: rare, and ztile_kernel's node
+// loop has to fit the instruction cache.  g: the segment's channel-independent values (ds, nrm0, nrm1, v0, v1);
+// returns the maser bits of the three channels (telescope.F:4295).
+__device__ __noinline__ unsigned zgeneral3(double *I3, const double *ep, const double *ec, const double *dtau,
+                                           const double *theo, const ZSeg &g) {
+  const uint32_t T1 = (uint32_t)__cvta_generic_to_shared(s_T1);
+  const double K0 = g.v0.kk * g.nrm0, A0 = g.v0.cN * g.nrm0, K1 = g.v1.kk * g.nrm1, A1 = g.v1.cN * g.nrm1;
+  const bool neg = g.v1.kk < 0.0;
+  unsigned mb = 0;
+#pragma unroll 1
+  for (int k = 0; k < 3; k++) {
+    const double alp1 = fma(K1, ec[k], g.v1.ad), src1 = fma(A1, ec[k], g.v1.sd);
+    const double alp0 = fma(K0, ep[k], g.v0.ad), src0 = fma(A0, ep[k], g.v0.sd);
+    double x, q;
+    step_onediv(alp0, src0, alp1, src1, dtau[k], theo[k], T1, x, q);
+    I3[k] = fma(I3[k], x, q);
+    if (neg && (K1 * ec[k]) * g.ds < (double)(-0.01f)) mb |= 1u << k;
+  }
+  return mb;
+}
+
 #ifndef RL_ZPIPE
 #define RL_ZPIPE 1
 #endif
@@ -1475,9 +1497,9 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
     for (int c = 0; c < cw; c++) {
       const double em = fmax(lds_f64(ep_a + 8u * (uint32_t)c), lds_f64(ec_a + 8u * (uint32_t)c));
       st[base]++;
-      if (em == 0.0) st[base + 1]++;
-      if (em <= 3.72e-44) st[base + 2]++;
-      if (em <= 1.6e-28) st[base + 3]++;
+      if (base && em == 0.0) st[base + 1]++;
+      if (base && em <= 3.72e-44) st[base + 2]++;
+      if (base && em <= 1.6e-28) st[base + 3]++;
     }
   };
 #endif
@@ -1617,6 +1639,8 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
         const double D = hds * (v0.ad + v1.ad), Th = hds * (v0.sd + v1.sd);
         const double Pq = hn0 * v0.kk, Q = hn1 * v1.kk, R = hn0 * v0.cN, S = hn1 * v1.cN;
         const bool neg = v1.kk < 0.0;  // inverted populations: full path, which carries the maser test
+        // lanes whose dust opacity alone is positive never see alpha <= 0 unless the line inverts
+        const bool nonpos = neg | !(v0.ad > kAlpMin) | !(v1.ad > kAlpMin) | (v0.kk < 0.0);
 #if RL_ZFAST
         // the profile is <= 1: if D + |P| + |Q| <= 1e-9 on every lane, every channel of the node takes the
         // thin branch of transfer.F:1522-1524,1545 (Q = theomax, xp = 1 - dtau): no votes, no branches, all
@@ -1663,12 +1687,11 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
               } else {
                 const double K0 = v0.kk * nrm0, A0 = v0.cN * nrm0, K1 = v1.kk * nrm1, A1 = v1.cN * nrm1;
 #if RL_ZSTREAM
-                // lanes whose dust opacity alone is positive never see alpha <= 0 unless the line inverts
-                const bool odd = neg | thin_some | !(v0.ad > kAlpMin) | !(v1.ad > kAlpMin) | (v0.kk < 0.0);
+                const bool anyodd = __any_sync(0xffffffffu, nonpos | thin_some);
 #ifdef RL_STATS
-                st[__any_sync(0xffffffffu, odd) ? 10 : 9]++;
+                st[anyodd ? 10 : 9]++;
 #endif
-                if (!__any_sync(0xffffffffu, odd)) {
+                if (!anyodd) {
                   // every lane: dtau > 1e-6 and both opacities positive -- qdr_src_2 without its case
                   // selections (the operations of step_coeffs on this branch, bit for bit)
 #pragma unroll
@@ -1691,24 +1714,43 @@ __global__ void __launch_bounds__(32 * kZWarps, RL_ZMINB * 2 / kZWarps) ztile_ke
 #endif
                     I[cb + k] = fma(I[cb + k], xpe, qv);
                   }
-                } else
-#endif
-                {
+                } else if (!__any_sync(0xffffffffu, nonpos)) {
+                  // both opacities positive on every lane, thin (dtau <= 1e-6) and thick channels in the group:
+                  // step_onediv with its opacity selections resolved (the same operations, bit for bit)
 #pragma unroll
                   for (int k = 0; k < 3; k++) {
                     const double alp1 = fma(K1, ec[k], v1.ad), src1 = fma(A1, ec[k], v1.sd);
                     const double alp0 = fma(K0, ep[k], v0.ad), src0 = fma(A0, ep[k], v0.sd);
-                    double x, q;
-#if RL_ZONEDIV
-                    step_onediv(alp0, src0, alp1, src1, dtau[k], theo[k], T1, x, q);
-#else
-                    const double r0 = div_fast(src0, alp0);
-                    double r1;
-                    step_coeffs(alp0, r0, src1, alp1, r1, dtau[k], theo[k], T1, x, q);
-#endif
-                    I[cb + k] = fma(I[cb + k], x, q);
-                    if (neg && (K1 * ec[k]) * nd->ds < (double)(-0.01f)) mbits |= 1u << (cb + k);  // telescope.F:4295
+                    const double xpe = expneg_tab(dtau[k], T1, 0);
+                    const double e0 = 1.0 - xpe, e1 = dtau[k] - e0;
+                    const bool thick = gt_mid(dtau[k]);
+                    const double hb = 0.5 * dtau[k];
+                    const double ca = thick ? fma(e0, dtau[k], -e1) : hb, cbb = thick ? e1 : hb;
+                    const double dd = thick ? dtau[k] : 1.0;
+                    const double den = dd * (alp0 * alp1);
+                    const double num = fma(ca, src0 * alp1, cbb * (src1 * alp0));
+                    const double x = thick ? xpe : (1.0 - dtau[k]);
+                    double qv = div_fast(num, den);
+                    qv = gt_thin(dtau[k]) ? min_sel(qv, theo[k]) : theo[k];
+                    I[cb + k] = fma(I[cb + k], x, qv);
                   }
+                } else
+#endif
+                {
+                  ZSeg sg;
+                  sg.ds = nd->ds;
+                  sg.nrm0 = nrm0;
+                  sg.nrm1 = nrm1;
+                  sg.v0 = v0;
+                  sg.v1 = v1;
+                  // (copies: the arrays of the hot paths must not have their address taken)
+                  double I3[3] = {I[cb], I[cb + 1], I[cb + 2]};
+                  const double ep3[3] = {ep[0], ep[1], ep[2]}, ec3[3] = {ec[0], ec[1], ec[2]};
+                  const double dt3[3] = {dtau[0], dtau[1], dtau[2]}, th3[3] = {theo[0], theo[1], theo[2]};
+                  mbits |= zgeneral3(I3, ep3, ec3, dt3, th3, sg) << cb;
+                  I[cb] = I3[0];
+                  I[cb + 1] = I3[1];
+                  I[cb + 2] = I3[2];
                 }
               }
             }
@@ -2378,8 +2420,15 @@ __global__ void zplan_kernel(RenderParams P) {
     const int4 *rg = P.rng + (size_t)ray * P.nl;
     const unsigned *ni = P.nitems + (size_t)ray * P.nl;
     unsigned short *zl = P.zlines + (size_t)ray * P.nl;
-    ZTile *out = FILL ? P.ztiles + P.cta_off[ray] : nullptr;
+    ZTile *out = FILL ? (P.ztiles_in ? P.ztiles_in : P.ztiles) + P.cta_off[ray] : nullptr;
     ZTile *outc = FILL ? P.ztiles + P.cta_off[P.nray + 1 + ray] : nullptr;
+    unsigned *outk = (FILL && P.zkeys) ? P.zkeys + P.cta_off[ray] : nullptr;
+    unsigned steps = 0;  // segments the ray's tiles walk (behind the opaque-wall start)
+    if (FILL && P.zkeys) {
+      const int N = (int)(P.node_off[ray + 1] - P.node_off[ray]);
+      const int ns = P.nstart ? max(1, min(P.nstart[ray], N - 1)) : 1;
+      steps = (unsigned)max(0, N - ns);
+    }
     auto emit = [&](int start, int cnt, int cmin, int cmax, bool cont) {
       if (cmax < cmin) { cmin = 1; cmax = 0; }
       const int nch = 1 + (cmax - cmin + 1);
@@ -2398,7 +2447,13 @@ __global__ void zplan_kernel(RenderParams P) {
           t.nlt = (unsigned char)cnt;
           t.lwshift = (unsigned char)lws;
           if (cont) outc[ncont] = t;
-          else out[n] = t;
+          else {
+            out[n] = t;
+            if (outk) {  // key: 4095 - work / 4, work = segments x (per-node part + channels per thread)
+              const unsigned cwt = ((unsigned)t.nchk + (32u >> lws) - 1u) >> (5 - lws);
+              outk[n] = 4095u - min(4095u, (steps * (2u + cwt)) >> 2);
+            }
+          }
         }
         if (cont) ncont++;
         else n++;

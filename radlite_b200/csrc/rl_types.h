@@ -192,6 +192,11 @@ struct RenderParams {
   int use_z;                 // 1: ztile_kernel (lines across lanes), 0: tile_kernel
   int zlw;                   // lines per ztile_kernel tile (power of two <= 32)
   ZTile *ztiles;             // [nztile] written by zplan_kernel<true>
+  // cost order (ztile_kernel): zplan_kernel<true> writes the general tiles to ztiles_in with a key that falls with
+  // the tile's work; a radix sort then leaves them in ztiles longest first, so that the last blocks of the launch
+  // are its shortest (null: the tiles stay in ray order)
+  ZTile *ztiles_in;
+  unsigned *zkeys;
   unsigned short *zlines;    // [nray][nl] per ray: the lines with a channel window, then the others
   unsigned nztile;
   CellMask *masks;           // [ncell]

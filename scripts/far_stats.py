@@ -14,7 +14,8 @@ for n in [int(a) for a in sys.argv[1:]] or [2]:
     buf = np.zeros(16, dtype=np.uint64); f(g.ctx, b"counters", buf.ctypes.data_as(C.c_void_p), 128)
     b = buf.astype(float)
     print("CFG", n, "R E S X", buf[:4])
-    print("  node-thin steps: channel slots", buf[4], "far@345/100/64", b[5:8] / max(1, b[4]))
+    print("  node-thin steps: channel slots", buf[4], "general groups that only mix thin and thick channels", buf[7],
+          "of", buf[14])
     print("  other unflagged steps: channel slots", buf[8], "far@345/100/64", b[9:12] / max(1, b[8]))
     print("  3-channel groups thin/stream/general", buf[12:15], "flagged node steps", buf[15])
     g.close()
