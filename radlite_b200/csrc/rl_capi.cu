@@ -666,6 +666,8 @@ static int ensure_geometry(rl_ctx *c, int ring_lo, int ring_hi, int kind = 0) {
     P.rstar = c->rstar;
     P.rbeam0_center = c->imcir_ri[1];
   }
+  P.costh0 = std::cos(P.theta0);
+  P.sinth0 = std::sin(P.theta0);
   P.in_itype = c->in_itype;
   P.cellS = c->d_cellS.p;
   P.status = c->d_status.p;

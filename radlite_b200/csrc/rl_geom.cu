@@ -214,9 +214,11 @@ __device__ NodePoint node_point(const GeomParams &P, double x0, double z0, doubl
   double sinphi;
   if (dummy > 0.0) sinphi = (bnew * bnew * costh0 - znew * snew) / dummy;
   else sinphi = 1.e1 * kTelescEps;
-  double phi = (x0 < 0.0) ? asin(sinphi) : (kPi - asin(sinphi));
-  while (phi < 0.0) phi = phi + 2.0 * kPi;
-  while (phi >= 2.0 * kPi) phi = phi - 2.0 * kPi;
+  // telescope.F:3702-3717 forms phi = asin(sinphi) (x0 < 0) or pi - asin(sinphi), wraps it into [0, 2 pi) and
+  // line.F:2659-2660 then takes sin(phi), cos(phi): sin(phi) is sinphi itself in both cases, cos(phi) = +-sqrt(1 - sinphi^2)
+  // -- two roundings instead of three libm calls per node (same conditioning near |sinphi| = 1)
+  const double cosphi_abs = sqrt(fmax(0.0, (1.0 - sinphi) * (1.0 + sinphi)));
+  const double cosphi = (x0 < 0.0) ? cosphi_abs : -cosphi_abs;
   // position inside the cell (telescope.F:3955-3958, 4088-4091)
   double dr = (radius - RCf(g, ir)) / (RCf(g, ir + 1) - RCf(g, ir));
   double dt = (theta - TCf(g, it)) / (TCf(g, it + 1) - TCf(g, it));
@@ -260,7 +262,7 @@ __device__ NodePoint node_point(const GeomParams &P, double x0, double z0, doubl
     }
   }
   if (mu > 1.0) atomicCAS(P.status, 0, 393);  // line.F:2656
-  o.dvmu = 3.335668e-11 * (mu * v1 + sqrt(1.0 - mu * mu) * (v2 * sin(phi) + v3 * cos(phi)));
+  o.dvmu = 3.335668e-11 * (mu * v1 + sqrt(1.0 - mu * mu) * (v2 * sinphi + v3 * cosphi));
   o.dr = dr;
   o.dt = dt;
   o.lw = lw;
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(256) node_kernel(GeomParams P, long long ntot)
   if (active) me = light[i];
   const int iray = me.iray;
   const double x0 = P.x0[iray], z0 = P.z0[iray];
-  const double costh0 = cos(P.theta0), sinth0 = sin(P.theta0);
+  const double costh0 = P.costh0, sinth0 = P.sinth0;
   const double sinth02 = sinth0 * sinth0;
   const double znew = z0 * sinth02;
   const double bnew = sqrt(x0 * x0 + z0 * z0 * sinth02);
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(256) roots_kernel(GeomParams P) {
   const int iray = P.ray_lo + rr;
   if (P.rect && iray > 0 && !(P.rb[iray] < P.bskip)) return;
   const double x0 = P.x0[iray], z0 = P.z0[iray];
-  const double costh0 = cos(P.theta0), sinth0 = sin(P.theta0);
+  const double costh0 = P.costh0, sinth0 = P.sinth0;
   const double costh02 = costh0 * costh0, sinth02 = sinth0 * sinth0;
   if (j < nth) {
     double a1, a2;
@@ -810,8 +812,8 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) geom_kernel(GeomParams P) {
   R.rstar = P.rstar;
   const double theta0 = P.theta0;
   R.pitheta0 = 0.5 * kPi - theta0;
-  R.costh0 = cos(theta0);
-  R.sinth0 = sin(theta0);
+  R.costh0 = P.costh0;
+  R.sinth0 = P.sinth0;
   R.costh02 = R.costh0 * R.costh0;
   R.sinth02 = R.sinth0 * R.sinth0;
   const double x0 = R.x0, z0 = R.z0;

@@ -97,6 +97,7 @@ struct GeomParams {
   const double *x0;  // [nray]
   const double *z0;
   double theta0;
+  double costh0, sinth0;  // cos / sin of theta0, evaluated once on the host (the reference's libm)
   double rstar;
   int in_itype;
   double rbeam0_center;  // imcir_ri(1): star mixing of the centre ray
