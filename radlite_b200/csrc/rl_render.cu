@@ -487,10 +487,14 @@ template <>
 __host__ __device__ constexpr double exp_coef<0>() {
   return 1.0;
 }
+// the same coefficients in constant memory: an FP64 instruction takes one operand straight from a constant bank,
+// while a 64-bit literal with a non-zero low word costs two UMOVs every time it is used (14 per three exp(-dtau))
+__constant__ double c_expc[9] = {exp_coef<0>(), exp_coef<1>(), exp_coef<2>(), exp_coef<3>(), exp_coef<4>(),
+                                 exp_coef<5>(), exp_coef<6>(), exp_coef<7>(), exp_coef<8>()};
 template <int K>
 struct Horner {
   static __device__ __forceinline__ double run(double p, double rp) {
-    return Horner<K - 1>::run(fma(p, rp, exp_coef<K>()), rp);
+    return Horner<K - 1>::run(fma(p, rp, c_expc[K]), rp);
   }
 };
 template <>
@@ -578,7 +582,7 @@ template <int DEG>
 __device__ __forceinline__ double exp_tab(double t, double rp, uint32_t T1) {
   const int n = __double2loint(t);
   const double v = lds_f64(T1 + ((n & (kTabN - 1)) << 3));
-  const double p = Horner<DEG - 1>::run(exp_coef<DEG>(), rp);
+  const double p = Horner<DEG - 1>::run(c_expc[DEG], rp);
   const int hi = __double2hiint(v) + ((n >> kTabBits) << 20);
   return __hiloint2double(hi, __double2loint(v)) * p;
 }
