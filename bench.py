@@ -169,13 +169,19 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clock / throttle-reason samples of one GPU.  The process is started before the warm-up (its start-up
+    takes longer than a short timed region), every row carries nvidia-smi's own timestamp, and ``stop()`` keeps the
+    rows that fall inside the timed region marked by ``mark()`` .. ``stop()``; if the region was shorter than the
+    sampling period and holds no row, the rows of the warm-up steps right before it (the same workload) are used and
+    ``window`` says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period_ms=200):
+    def __init__(self, index, period_ms=50):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = time.time()
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", str(period_ms), "-i", str(index)], stdout=self.f,
@@ -183,7 +189,20 @@ class ClockSampler:
         except OSError:
             pass
 
+    def mark(self):
+        """Start of the timed region."""
+        self.t0 = time.time()
+
+    @staticmethod
+    def _stamp(txt):
+        import datetime
+        try:
+            return datetime.datetime.strptime(txt.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def stop(self):
+        t1 = time.time()
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -196,11 +215,19 @@ class ClockSampler:
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        stamps = [self._stamp(r[0]) for r in rows]
+        inside = [r for r, t in zip(rows, stamps) if t is not None and self.t0 <= t <= t1]
+        window = "timed region"
+        if not inside:  # shorter than the sampling period: the last warm-up steps (same workload) stand in
+            before = [r for r, t in zip(rows, stamps) if t is not None and self.t0 - 1.0 <= t <= t1 + 0.05]
+            inside = before or rows[-3:]
+            window = "last warm-up steps + timed region (the timed region is shorter than the sampling period)"
+        rows = inside
         sm = sorted(float(r[1]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if "Active" in v and "Not" not in v})
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
-                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows), "window": window}
 
 
 def run_gpu(args):
@@ -258,12 +285,13 @@ def run_gpu(args):
     strong = world > 1
     sampler = None
     if not strong:
+        sampler = ClockSampler(local, args.clock_ms)  # (started here: see the class)
         for _ in range(args.warmup):
             step_device()
         g.reset_counters()
         l0 = g.launch_count()
-        sampler = ClockSampler(local, args.clock_ms)
         barrier()
+        sampler.mark()
         t0 = time.perf_counter()
         ms = np.zeros(5)
         for _ in range(K):
@@ -351,11 +379,14 @@ def run_gpu(args):
             recuts += 1
         blocks = best[1]
         lo, hi = blocks[rank]
-        step_strong()
+        sampler = ClockSampler(local, args.clock_ms) if rank == 0 else None  # (started here: see the class)
+        for _ in range(3):
+            step_strong()
         g.reset_counters()
         l0 = g.launch_count()
-        sampler = ClockSampler(local, args.clock_ms) if rank == 0 else None
         barrier()
+        if sampler:
+            sampler.mark()
         t0 = time.perf_counter()
         ms = np.zeros(5)
         for _ in range(K):
@@ -496,8 +527,9 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based)")
     ap.add_argument("--lines", type=int, default=None, help="override the number of lines of the spectrum")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--clock-ms", type=int, default=200, help="nvidia-smi sampling period during the timed region "
-                    "(B200_PROFILING.md recipe: 200 ms)")
+    ap.add_argument("--clock-ms", type=int, default=50, help="nvidia-smi sampling period (B200_PROFILING.md recipe: "
+                    "200 ms; 50 so that the 60 ms timed region of an 8-GPU run still holds a sample -- no effect on "
+                    "the timing was measured between 100 ms and none at all)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE line, the JSON result: anything libraries print there (NCCL's version
