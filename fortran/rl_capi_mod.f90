@@ -68,7 +68,7 @@ module rl_capi_mod
        integer(c_int), value :: subgrid, nonredundant
        real(c_double), value :: levthres, aksmax
      end function
-     ! opaque-wall start (include/radlite_b200.h): 0 integrates every segment like the reference; default 150
+     ! opaque-wall start (include/radlite_b200.h): 0 integrates every segment like the reference; default 64
      integer(c_int) function rl_set_wall_tau(ctx, tau) bind(c, name='rl_set_wall_tau')
        import :: c_ptr, c_int, c_double
        type(c_ptr), value :: ctx

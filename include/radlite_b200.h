@@ -187,11 +187,14 @@ int rl_synthesize_spectrum(rl_ctx *ctx, int nl, int nfr, const double *vel, cons
 void rl_get_counters(const rl_ctx *ctx, double *R, double *E, double *S);
 void rl_reset_counters(rl_ctx *ctx);
 /* Opaque-wall start (no counterpart in the reference, which integrates every segment of a ray,
- * telescope.F:4079-4300): segments that lie behind more than `tau` of dust optical depth -- for every
- * line of the batch, counted from the observer's end of the ray -- are not integrated; what they would
- * contribute is attenuated by exp(-tau).  Default 150 (a relative 1e-65: far below the rounding of the
- * result); 0 integrates every segment.  R, E, S above keep counting the reference's work;
- * rl_get_executed returns the element integrations this library actually performed. */
+ * telescope.F:4079-4300): the segments of a ray that lie, seen from the observer, behind so much dust optical
+ * depth that their contribution is provably below exp(-tau) of what the dust in front of them emits -- for
+ * every line of the batch; criterion in DESIGN.md 4.3: upper bound of the dropped part against a lower bound
+ * of the kept part -- are not integrated.  Default 64 (a relative 1e-28: twelve orders of magnitude below the
+ * rounding of the result); a batch with an inverted level pair or a negative dust opacity, and a ray whose
+ * front crosses a cell without emission, are never shortened; 0 integrates every segment.  R, E, S above
+ * keep counting the reference's work; rl_get_executed returns the element integrations this library
+ * actually performed. */
 int rl_set_wall_tau(rl_ctx *ctx, double tau);
 /* Integrate kernel: 0 = chosen by regime (ztile_kernel + zcont_kernel from 8 lines per batch, chan_kernel
  * below), 1 = ztile_kernel, 2 = tile_kernel, 3 = chan_kernel.  ztile_kernel and chan_kernel give the same bits,
